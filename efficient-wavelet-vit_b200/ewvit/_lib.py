@@ -24,6 +24,10 @@ SIGNATURES = {
     "ewvit_launch_count": (c_uint64, []),
     "ewvit_dwt_haar_fwd": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ewvit_dwt3_haar_fwd": (c_int, [c_void_p, c_int64, c_int, c_int] + [c_void_p] * 6 + [c_void_p]),
+    "ewvit_linear_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int,
+                                  c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "ewvit_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 

@@ -82,6 +82,47 @@ EWVIT_API int ewvit_dwt3_haar_fwd(const float *x, int64_t planes, int h, int w,
                         float *ll1, float *hf1, float *ll2, float *hf2, float *ll3, float *hf3,
                         void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * bf16 tensor-core linear layer  (rows a-5, a-7: nn.Linear call sites network/sfe.py:155 patch_to_embedding,
+ * sfe.py:52,54 to_qkv/to_out, sfe.py:31-37 FeedForward, sfe.py:141 feat_map; all `x @ W^T + b`)
+ *
+ *   out[M, N] = act( (A[M, K] @ W[N, K]^T) * scale[N] + shift[N] + residual[M, N] )
+ *
+ *   a        [M, K]  bf16 row-major            w  [N, K] bf16 row-major (the nn.Linear weight as stored)
+ *   scale    [N] fp32 or NULL (= 1)            shift [N] fp32 or NULL (= 0; the bias)
+ *   act      0 none, 1 ReLU, 2 GELU (erf)      residual [M, ldr] fp32 or NULL (added BEFORE act)
+ *   out      [M, ldo] bf16 (out_fp32 = 0) or fp32 (out_fp32 = 1)
+ *   splits   > 1 selects split-K: `workspace` must hold splits*M*N floats; partial sums are reduced
+ *            in a fixed order (deterministic).
+ * Needs K % 64 == 0 and N % 128 == 0.  fp32 accumulation in TMEM (tcgen05.mma kind::f16).
+ * ------------------------------------------------------------------------------------------- */
+EWVIT_API int ewvit_linear_bf16(const void *a, const void *w, int64_t M, int N, int K,
+                                const float *scale, const float *shift, int act,
+                                const float *residual, int64_t ldr,
+                                void *out, int out_fp32, int64_t ldo,
+                                int splits, float *workspace, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 3x3 convolution, padding 1, stride 1 or 2, as a bf16 implicit GEMM with a fused per-channel
+ * scale/shift (folded conv bias + eval-mode BatchNorm) and ReLU  (rows a-3, a-4: the Conv2d+BatchNorm2d+
+ * ReLU triples at reference network/mwt.py:33-36 freq_conv, :40-42 freq_pool, :60-64 hf_conv.fusion,
+ * :68-72 multiscale_fusion).
+ *
+ *   x  NHWC bf16: [n, h, wd, cin], or with in_padded = 1 [n, h+2, wd+2, cin] carrying an explicit zero border
+ *   w  [cout, 3, 3, cin] bf16 (tap-major K: k = (ky*3 + kx)*cin + c)
+ *   y  NHWC bf16 with channel pitch y_ldc, written at channel offset y_coff (lets three producers fill
+ *      one concatenated buffer, mwt.py:113): [n, ho, wo, y_ldc], or with out_padded = 1
+ *      [n, ho+2, wo+2, y_ldc];  ho = (h-1)/stride + 1
+ *   y[.., co] = relu?( conv(x, w)[.., co] * scale[co] + shift[co] )
+ * stride 1 with in_padded = out_padded = 1 takes the row-shift path and ALSO writes the zero border of y;
+ * every other combination takes the box path (stride-2 via the TMA element stride) and writes interior
+ * pixels only (a padded y must have been zeroed once by the caller).  force_tiled = 1 forces the box path.
+ * Needs cin % 64 == 0 and cout % 128 == 0.
+ * ------------------------------------------------------------------------------------------- */
+EWVIT_API int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, int wd, int cin, int cout,
+                                 int stride, int in_padded, const float *scale, const float *shift, int relu,
+                                 void *y, int y_ldc, int y_coff, int out_padded, int force_tiled, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
