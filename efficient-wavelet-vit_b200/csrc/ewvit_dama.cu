@@ -1,0 +1,279 @@
+// DAMA fusion tail: bidirectional cross-attention over the
+// 1x1 spatial / frequency tokens, centre-tap fusion gate, softmax(3) adaptive gate, weighted sum, per-video
+// mean and the classifier.  One fused kernel instead of ~60 tiny eager launches; per frame this is ~0.4 MFLOP
+// of 128-wide mat-vecs, so it runs on CUDA cores in fp32 (no precision loss against the fp32 reference) with
+// the (pre-transposed) weights streamed from L2 and shared by the frames of a CTA.
+#include "ewvit_common.cuh"
+
+namespace {
+
+constexpr int kFpc = 4;   // frames per CTA
+
+struct DamaParams {
+    const float *space_in, *freq_in;   // [n, D]
+    const float *wpack;                // packed weights, layout in include/ewvit.h
+    float *fused, *space, *freq;       // [n, D] outputs
+    long long n;
+    int d, heads, depth;
+    float ln_eps;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// y[f][j] = sum_k Wt[k*ldw + j] * x[f][k]   for the kFpc frames of the CTA (x in shared memory)
+__device__ __forceinline__ void matvec_t(const float *__restrict__ wt, int ldw, int in_dim, const float *x, int ldx, int j,
+                                         float (&acc)[kFpc]) {
+#pragma unroll
+    for (int f = 0; f < kFpc; ++f) acc[f] = 0.f;
+    for (int k = 0; k < in_dim; ++k) {
+        const float w = __ldg(wt + (long long)k * ldw + j);
+#pragma unroll
+        for (int f = 0; f < kFpc; ++f) acc[f] = fmaf(w, x[f * ldx + k], acc[f]);
+    }
+}
+
+__global__ void dama_tail_kernel(const DamaParams p) {
+    extern __shared__ float sm[];
+    const int D = p.d, j = threadIdx.x;
+    float *s_s = sm;                 // [kFpc][D] spatial tokens
+    float *s_f = s_s + kFpc * D;     // frequency tokens
+    float *s_xn = s_f + kFpc * D;    // normalised query tokens
+    float *s_q = s_xn + kFpc * D;
+    float *s_k0 = s_q + kFpc * D, *s_k1 = s_k0 + kFpc * D, *s_v0 = s_k1 + kFpc * D, *s_v1 = s_v0 + kFpc * D;
+    float *s_p0 = s_v1 + kFpc * D, *s_p1 = s_p0 + kFpc * D;   // per-channel q*k products
+    float *s_att = s_p1 + kFpc * D;
+    float *s_cat = s_att + kFpc * D;   // [kFpc][2D]
+    float *s_hid = s_cat + kFpc * 2 * D;   // [kFpc][D/2]
+    float *s_gate = s_hid + kFpc * (D / 2);   // [kFpc][4]
+
+    const long long f0 = (long long)blockIdx.x * kFpc;
+    const int nwarps = blockDim.x >> 5, warp = j >> 5, lane = j & 31;
+    const int dh = D / p.heads;
+    const float scale = rsqrtf((float)dh);
+
+#pragma unroll
+    for (int f = 0; f < kFpc; ++f) {
+        const long long fr = f0 + f;
+        s_s[f * D + j] = fr < p.n ? p.space_in[fr * D + j] : 0.f;
+        s_f[f * D + j] = fr < p.n ? p.freq_in[fr * D + j] : 0.f;
+    }
+    __syncthreads();
+
+    const long long blk = 4LL * D * D + 3LL * D;
+    for (int l = 0; l < p.depth; ++l) {
+        for (int dir = 0; dir < 2; ++dir) {
+            const float *wb = p.wpack + (l * 2 + dir) * blk;
+            const float *ln_w = wb, *ln_b = wb + D, *wq_t = wb + 2 * D, *wkv_t = wq_t + (long long)D * D;
+            const float *wo_t = wkv_t + 2LL * D * D, *bo = wo_t + (long long)D * D;
+            float *xq = dir == 0 ? s_s : s_f;     // query stream (updated in place)
+            float *ctx = dir == 0 ? s_f : s_s;    // context: the other stream (dir 1 sees the UPDATED spatial tokens)
+
+            // LayerNorm of the query tokens (dama.py:71,75), one warp per frame
+            for (int f = warp; f < kFpc; f += nwarps) {
+                float s = 0.f;
+                for (int c = lane; c < D; c += 32) s += xq[f * D + c];
+                const float mean = warp_sum(s) / (float)D;
+                float v = 0.f;
+                for (int c = lane; c < D; c += 32) {
+                    const float t = xq[f * D + c] - mean;
+                    v += t * t;
+                }
+                const float rstd = rsqrtf(warp_sum(v) / (float)D + p.ln_eps);
+                for (int c = lane; c < D; c += 32) s_xn[f * D + c] = (xq[f * D + c] - mean) * rstd * ln_w[c] + ln_b[c];
+            }
+            __syncthreads();
+
+            // q from the normalised tokens; k/v from cat(normalised tokens, raw context) (dama.py:38-42)
+            float acc[kFpc], acc2[kFpc];
+            matvec_t(wq_t, D, D, s_xn, D, j, acc);
+#pragma unroll
+            for (int f = 0; f < kFpc; ++f) s_q[f * D + j] = acc[f];
+            matvec_t(wkv_t, 2 * D, D, s_xn, D, j, acc);
+            matvec_t(wkv_t, 2 * D, D, ctx, D, j, acc2);
+#pragma unroll
+            for (int f = 0; f < kFpc; ++f) { s_k0[f * D + j] = acc[f]; s_k1[f * D + j] = acc2[f]; }
+            matvec_t(wkv_t + D, 2 * D, D, s_xn, D, j, acc);
+            matvec_t(wkv_t + D, 2 * D, D, ctx, D, j, acc2);
+#pragma unroll
+            for (int f = 0; f < kFpc; ++f) { s_v0[f * D + j] = acc[f]; s_v1[f * D + j] = acc2[f]; }
+#pragma unroll
+            for (int f = 0; f < kFpc; ++f) {
+                s_p0[f * D + j] = s_q[f * D + j] * s_k0[f * D + j];
+                s_p1[f * D + j] = s_q[f * D + j] * s_k1[f * D + j];
+            }
+            __syncthreads();
+
+            // 1 query x 2 keys per head: softmax over the two dots (dama.py:44-48)
+            const int h0 = (j / dh) * dh;
+#pragma unroll
+            for (int f = 0; f < kFpc; ++f) {
+                float d0 = 0.f, d1 = 0.f;
+                for (int c = 0; c < dh; ++c) {
+                    d0 += s_p0[f * D + h0 + c];
+                    d1 += s_p1[f * D + h0 + c];
+                }
+                d0 *= scale;
+                d1 *= scale;
+                const float m = fmaxf(d0, d1);
+                const float e0 = expf(d0 - m), e1 = expf(d1 - m);
+                const float inv = 1.f / (e0 + e1);
+                s_att[f * D + j] = (e0 * inv) * s_v0[f * D + j] + (e1 * inv) * s_v1[f * D + j];
+            }
+            __syncthreads();
+
+            matvec_t(wo_t, D, D, s_att, D, j, acc);
+            const float b = bo[j];
+#pragma unroll
+            for (int f = 0; f < kFpc; ++f) xq[f * D + j] += acc[f] + b;   // residual (dama.py:72,76)
+            __syncthreads();
+        }
+    }
+
+    // ---- fusion gate: 3x3 conv on a 1x1 map == its centre tap (dama.py:124-128,153), folded BN, ReLU
+    const float *wf_t = p.wpack + (long long)p.depth * 2 * blk;
+    const float *f_scale = wf_t + 2LL * D * D, *f_shift = f_scale + D;
+    const float *g1_t = f_shift + D, *g1_b = g1_t + 2LL * D * (D / 2);
+    const float *g2 = g1_b + D / 2, *g2_b = g2 + 3 * (D / 2);
+#pragma unroll
+    for (int f = 0; f < kFpc; ++f) {
+        s_cat[f * 2 * D + j] = s_s[f * D + j];
+        s_cat[f * 2 * D + D + j] = s_f[f * D + j];
+    }
+    __syncthreads();
+    float fused[kFpc];
+    matvec_t(wf_t, D, 2 * D, s_cat, 2 * D, j, fused);
+#pragma unroll
+    for (int f = 0; f < kFpc; ++f) fused[f] = fmaxf(fmaf(fused[f], f_scale[j], f_shift[j]), 0.f);
+
+    // ---- gate_net: Linear(2D -> D/2) + ReLU, Linear(D/2 -> 3), softmax (dama.py:105-113,156-157)
+    if (j < D / 2) {
+        float acc[kFpc];
+        matvec_t(g1_t, D / 2, 2 * D, s_cat, 2 * D, j, acc);
+#pragma unroll
+        for (int f = 0; f < kFpc; ++f) s_hid[f * (D / 2) + j] = fmaxf(acc[f] + g1_b[j], 0.f);
+    }
+    __syncthreads();
+    for (int f = warp; f < kFpc; f += nwarps) {
+        float z[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            float s = 0.f;
+            for (int c = lane; c < D / 2; c += 32) s += g2[o * (D / 2) + c] * s_hid[f * (D / 2) + c];
+            z[o] = warp_sum(s) + g2_b[o];
+        }
+        const float m = fmaxf(z[0], fmaxf(z[1], z[2]));
+        const float e0 = expf(z[0] - m), e1 = expf(z[1] - m), e2 = expf(z[2] - m);
+        const float inv = 1.f / (e0 + e1 + e2);
+        if (lane == 0) {
+            s_gate[f * 4 + 0] = e0 * inv;
+            s_gate[f * 4 + 1] = e1 * inv;
+            s_gate[f * 4 + 2] = e2 * inv;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int f = 0; f < kFpc; ++f) {
+        const long long fr = f0 + f;
+        if (fr < p.n) {
+            const float sv = s_s[f * D + j], fv = s_f[f * D + j];
+            p.fused[fr * D + j] = s_gate[f * 4] * sv + s_gate[f * 4 + 1] * fv + s_gate[f * 4 + 2] * fused[f];   // dama.py:159-163
+            p.space[fr * D + j] = sv;
+            p.freq[fr * D + j] = fv;
+        }
+    }
+}
+
+// Per-video mean over K consecutive frames (dama.py:188-199) and, when cw1 != nullptr, the classifier
+// Linear(D->Hc)+ReLU+Linear(Hc->1) on the first feature set (model.py:62-68,92).  One CTA per video.
+__global__ void video_head_kernel(const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ c,
+                                  int k, int d, float *__restrict__ ma, float *__restrict__ mb, float *__restrict__ mc,
+                                  const float *__restrict__ cw1, const float *__restrict__ cb1, const float *__restrict__ cw2,
+                                  const float *__restrict__ cb2, int hc, float *__restrict__ logits) {
+    extern __shared__ float sm[];
+    float *s_mean = sm, *s_hid = sm + d;
+    const long long v = blockIdx.x;
+    const int j = threadIdx.x;
+    const float *src[3] = {a, b, c};
+    float *dst[3] = {ma, mb, mc};
+    for (int t = 0; t < 3; ++t) {
+        if (!src[t]) continue;
+        for (int ch = j; ch < d; ch += blockDim.x) {
+            float s = 0.f;
+            for (int i = 0; i < k; ++i) s += src[t][(v * k + i) * d + ch];
+            s /= (float)k;
+            dst[t][v * d + ch] = s;
+            if (t == 0) s_mean[ch] = s;
+        }
+    }
+    if (!cw1) return;
+    __syncthreads();
+    for (int o = j; o < hc; o += blockDim.x) {
+        float s = cb1[o];
+        for (int ch = 0; ch < d; ++ch) s = fmaf(cw1[(long long)o * d + ch], s_mean[ch], s);
+        s_hid[o] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    if (j < 32) {
+        float s = 0.f;
+        for (int o = j; o < hc; o += 32) s += cw2[o] * s_hid[o];
+        s = warp_sum(s);
+        if (j == 0) logits[v] = s + cb2[0];
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t ewvit_dama_wpack_floats(int d, int depth) {
+    const int64_t D = d;
+    return (int64_t)depth * 2 * (4 * D * D + 3 * D) + 2 * D * D + 2 * D + 2 * D * (D / 2) + D / 2 + 3 * (D / 2) + 3;
+}
+
+extern "C" int ewvit_dama_tail_fwd(const float *space_in, const float *freq_in, int64_t n, int d, int heads, int depth,
+                                   const float *wpack, float ln_eps, float *fused, float *space, float *freq,
+                                   void *stream) {
+    EWVIT_REQUIRE(n >= 0 && d > 0 && heads > 0 && depth > 0, EWVIT_ERR_INVALID_ARG, "ewvit_dama_tail_fwd: bad sizes");
+    EWVIT_REQUIRE(d % 32 == 0 && d <= 512 && d % heads == 0, EWVIT_ERR_UNSUPPORTED,
+                  "ewvit_dama_tail_fwd: dim must be a multiple of 32 (<= 512) and divisible by heads (got dim=%d heads=%d)", d, heads);
+    if (n == 0) return EWVIT_OK;
+    EWVIT_REQUIRE(space_in && freq_in && wpack && fused && space && freq, EWVIT_ERR_INVALID_ARG, "ewvit_dama_tail_fwd: NULL pointer");
+    int rc = ewvit_check_device();
+    if (rc != EWVIT_OK) return rc;
+    DamaParams p;
+    p.space_in = space_in; p.freq_in = freq_in; p.wpack = wpack; p.fused = fused; p.space = space; p.freq = freq;
+    p.n = n; p.d = d; p.heads = heads; p.depth = depth; p.ln_eps = ln_eps;
+    const size_t smem = (size_t)(kFpc * d * 11 + kFpc * 2 * d + kFpc * (d / 2) + kFpc * 4) * sizeof(float);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    EWVIT_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(dama_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    dama_tail_kernel<<<(unsigned)((n + kFpc - 1) / kFpc), d, smem, (cudaStream_t)stream>>>(p);
+    EWVIT_LAUNCH_OK();
+    return EWVIT_OK;
+}
+
+extern "C" int ewvit_video_head_fwd(const float *fused, const float *space, const float *freq, int64_t videos, int k, int d,
+                                    float *mean_fused, float *mean_space, float *mean_freq, const float *cw1,
+                                    const float *cb1, const float *cw2, const float *cb2, int hc, float *logits,
+                                    void *stream) {
+    EWVIT_REQUIRE(videos >= 0 && k > 0 && d > 0, EWVIT_ERR_INVALID_ARG, "ewvit_video_head_fwd: bad sizes");
+    if (videos == 0) return EWVIT_OK;
+    EWVIT_REQUIRE(fused && mean_fused, EWVIT_ERR_INVALID_ARG, "ewvit_video_head_fwd: NULL pointer");
+    EWVIT_REQUIRE((space == nullptr) == (mean_space == nullptr) && (freq == nullptr) == (mean_freq == nullptr),
+                  EWVIT_ERR_INVALID_ARG, "ewvit_video_head_fwd: each optional input needs its output");
+    EWVIT_REQUIRE(!cw1 || (cb1 && cw2 && cb2 && logits && hc > 0), EWVIT_ERR_INVALID_ARG,
+                  "ewvit_video_head_fwd: incomplete classifier arguments");
+    int rc = ewvit_check_device();
+    if (rc != EWVIT_OK) return rc;
+    const size_t smem = (size_t)(d + (hc > 0 ? hc : 0)) * sizeof(float);
+    video_head_kernel<<<(unsigned)videos, 128, smem, (cudaStream_t)stream>>>(fused, space, freq, k, d, mean_fused, mean_space,
+                                                                            mean_freq, cw1, cb1, cw2, cb2, hc, logits);
+    EWVIT_LAUNCH_OK();
+    return EWVIT_OK;
+}

@@ -1,0 +1,250 @@
+// MWT glue kernels around the tensor-core convs.
+//
+//  * mwt_head: high-frequency subbands of one level  ->  bilinear upsample to the level-1 grid
+//    (F.interpolate, mwt.py:79-81)  ->  the three per-colour Conv2d(3->18,3x3,p1)+BN+ReLU
+//    (hf_conv['seperate'], mwt.py:84-86)  ->  concatenated 54 channels, written as the bf16
+//    "padded-flat" NHWC tensor [N, H+2, W+2, 64] (channels 54..63 zero) that the 54->128 fusion conv
+//    consumes through TMA.  K = 27 per group is far too skinny for tensor cores: CUDA cores, fp32.
+//  * maxpool2x2 (freq_pool[0], mwt.py:39) and the global average pool (freq_pool[4], mwt.py:43) on
+//    NHWC bf16.
+#include "ewvit_common.cuh"
+
+namespace {
+
+constexpr int kTile = 16;               // 16x16 output pixels per CTA
+constexpr int kHalo = kTile + 2;        // 18
+constexpr int kHaloPitch = 20;
+constexpr int kHeadThreads = 192;       // 64 pixel quads x 3 colour groups
+constexpr int kOcPerGroup = 18;
+constexpr int kWPitch = 28;             // 27 weights per output channel, padded to 7 float4
+constexpr int kOutC = 64;               // 54 real + 10 zero channels
+constexpr int kUpBytes = 9 * kHalo * kHaloPitch * 4;                    // 12960
+constexpr int kWBytes = (3 * kOcPerGroup * kWPitch + 2 * 56) * 4;       // 6496
+constexpr int kHeadSmem = kUpBytes + kWBytes + kTile * kTile * kOutC * 2;   // 52224
+
+struct HeadParams {
+    const float *hf;      // [n, 9, hin, win]  (colour-major, subband-minor: the reference's reshape at mwt.py:77)
+    const float *w;       // [3 groups][18][3][3][3]
+    const float *scale;   // [54] folded BN scale
+    const float *shift;   // [54] folded conv bias + BN shift
+    __nv_bfloat16 *y;     // [n, hout+2, wout+2, 64]
+    int n, hin, win, hout, wout;
+    float ry, rx;         // hin/hout, win/wout (PyTorch area_pixel_compute_scale, align_corners=False)
+};
+
+// PyTorch bilinear source index (align_corners=False): max(0, scale*(dst+0.5)-0.5)
+__device__ __forceinline__ void src_index(int dst, float scale, int in_size, int &i0, int &i1, float &l1) {
+    float s = scale * (dst + 0.5f) - 0.5f;
+    s = s < 0.f ? 0.f : s;
+    i0 = (int)s;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+}
+
+__global__ void __launch_bounds__(kHeadThreads) mwt_head_kernel(const HeadParams p) {
+    extern __shared__ __align__(16) unsigned char head_smem[];
+    float (*s_up)[kHalo][kHaloPitch] = reinterpret_cast<float (*)[kHalo][kHaloPitch]>(head_smem);
+    float *s_w = reinterpret_cast<float *>(head_smem + kUpBytes);
+    float *s_scale = s_w + 3 * kOcPerGroup * kWPitch;
+    float *s_shift = s_scale + 56;
+    __nv_bfloat16 (*s_out)[kOutC] = reinterpret_cast<__nv_bfloat16 (*)[kOutC]>(head_smem + kUpBytes + kWBytes);
+
+    const int tid = threadIdx.x;
+    const int tiles_x = (p.wout + kTile - 1) / kTile;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
+    const int img = blockIdx.y;
+    const int y0 = ty * kTile, x0 = tx * kTile;
+
+    for (int i = tid; i < 3 * kOcPerGroup * kWPitch; i += kHeadThreads) {
+        const int oc = i / kWPitch, k = i % kWPitch;
+        s_w[i] = k < 27 ? p.w[oc * 27 + k] : 0.f;
+    }
+    if (tid < 54) {
+        s_scale[tid] = p.scale[tid];
+        s_shift[tid] = p.shift[tid];
+    }
+    // upsampled halo tile (zero outside the image: the conv's padding)
+    const float *src = p.hf + (long long)img * 9 * p.hin * p.win;
+    const bool same = (p.hin == p.hout) && (p.win == p.wout);
+    for (int i = tid; i < 9 * kHalo * kHalo; i += kHeadThreads) {
+        const int c = i / (kHalo * kHalo), rem = i % (kHalo * kHalo);
+        const int hy = rem / kHalo, hx = rem % kHalo;
+        const int oy = y0 + hy - 1, ox = x0 + hx - 1;
+        float v = 0.f;
+        if (oy >= 0 && oy < p.hout && ox >= 0 && ox < p.wout) {
+            const float *pc = src + (long long)c * p.hin * p.win;
+            if (same) {
+                v = pc[oy * p.win + ox];
+            } else {
+                int ya, yb, xa, xb;
+                float ly, lx;
+                src_index(oy, p.ry, p.hin, ya, yb, ly);
+                src_index(ox, p.rx, p.win, xa, xb, lx);
+                const float v00 = pc[ya * p.win + xa], v01 = pc[ya * p.win + xb];
+                const float v10 = pc[yb * p.win + xa], v11 = pc[yb * p.win + xb];
+                v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+            }
+        }
+        s_up[c][hy][hx] = v;
+    }
+    __syncthreads();
+
+    // ---- 3 -> 18 conv for one colour group on a quad of 4 horizontally adjacent pixels
+    {
+        const int g = tid / 64, quad = tid % 64;
+        const int qy = quad / 4, qx = (quad % 4) * 4;
+        float in[3][3][6];
+#pragma unroll
+        for (int ic = 0; ic < 3; ++ic)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 6; ++dx) in[ic][dy][dx] = s_up[g * 3 + ic][qy + dy][qx + dx];
+#pragma unroll 2
+        for (int oc = 0; oc < kOcPerGroup; ++oc) {
+            const float4 *wp = reinterpret_cast<const float4 *>(&s_w[(g * kOcPerGroup + oc) * kWPitch]);
+            float wv[28];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const float4 t = wp[i];
+                wv[4 * i] = t.x; wv[4 * i + 1] = t.y; wv[4 * i + 2] = t.z; wv[4 * i + 3] = t.w;
+            }
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int ic = 0; ic < 3; ++ic)
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const float wk = wv[ic * 9 + dy * 3 + dx];
+                        a0 = fmaf(wk, in[ic][dy][dx], a0);
+                        a1 = fmaf(wk, in[ic][dy][dx + 1], a1);
+                        a2 = fmaf(wk, in[ic][dy][dx + 2], a2);
+                        a3 = fmaf(wk, in[ic][dy][dx + 3], a3);
+                    }
+            const int ch = g * kOcPerGroup + oc;
+            const float sc = s_scale[ch], sh = s_shift[ch];
+            const int px = qy * kTile + qx;
+            s_out[px + 0][ch] = __float2bfloat16_rn(fmaxf(fmaf(a0, sc, sh), 0.f));
+            s_out[px + 1][ch] = __float2bfloat16_rn(fmaxf(fmaf(a1, sc, sh), 0.f));
+            s_out[px + 2][ch] = __float2bfloat16_rn(fmaxf(fmaf(a2, sc, sh), 0.f));
+            s_out[px + 3][ch] = __float2bfloat16_rn(fmaxf(fmaf(a3, sc, sh), 0.f));
+        }
+        if (g == 2) {
+            const int px = qy * kTile + qx;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int ch = 54; ch < kOutC; ++ch) s_out[px + k][ch] = __float2bfloat16_rn(0.f);
+        }
+    }
+    __syncthreads();
+
+    // ---- coalesced 16-byte stores: one output pixel = 128 contiguous bytes of the NHWC tensor
+    const int wp_ = p.wout + 2;
+    __nv_bfloat16 *ybase = p.y + (long long)img * (p.hout + 2) * wp_ * kOutC;
+    for (int i = tid; i < kTile * kTile * 8; i += kHeadThreads) {
+        const int px = i / 8, part = i % 8;
+        const int oy = y0 + px / kTile, ox = x0 + px % kTile;
+        if (oy < p.hout && ox < p.wout) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(&s_out[px][part * 8]);
+            *reinterpret_cast<uint4 *>(ybase + ((long long)(oy + 1) * wp_ + (ox + 1)) * kOutC + part * 8) = v;
+        }
+    }
+}
+
+// 2x2/stride-2 max pool on NHWC bf16; 8 channels (16 bytes) per thread.
+__global__ void maxpool2x2_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ y, long long n, int h,
+                                  int w, int c) {
+    const int ho = h / 2, wo = w / 2, c8 = c / 8;
+    const long long total = n * ho * wo * c8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % c8);
+        long long t = i / c8;
+        const int ox = (int)(t % wo);
+        t /= wo;
+        const int oy = (int)(t % ho);
+        const long long img = t / ho;
+        const __nv_bfloat16 *p00 = x + ((img * h + 2 * oy) * w + 2 * ox) * c + cc * 8;
+        uint4 a = *reinterpret_cast<const uint4 *>(p00), b = *reinterpret_cast<const uint4 *>(p00 + c);
+        uint4 d = *reinterpret_cast<const uint4 *>(p00 + (long long)w * c), e = *reinterpret_cast<const uint4 *>(p00 + (long long)w * c + c);
+        uint4 r;
+        const __nv_bfloat162 *pa = reinterpret_cast<const __nv_bfloat162 *>(&a), *pb = reinterpret_cast<const __nv_bfloat162 *>(&b);
+        const __nv_bfloat162 *pd = reinterpret_cast<const __nv_bfloat162 *>(&d), *pe = reinterpret_cast<const __nv_bfloat162 *>(&e);
+        __nv_bfloat162 *pr = reinterpret_cast<__nv_bfloat162 *>(&r);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pr[k] = __hmax2(__hmax2(pa[k], pb[k]), __hmax2(pd[k], pe[k]));
+        *reinterpret_cast<uint4 *>(y + ((img * ho + oy) * wo + ox) * c + cc * 8) = r;
+    }
+}
+
+// Global average pool over hw pixels: x [n, hw, c] bf16 -> y [n, ldy] fp32 at channel offset.
+__global__ void gap_kernel(const __nv_bfloat16 *__restrict__ x, float *__restrict__ y, int hw, int c, long long ldy) {
+    const long long img = blockIdx.x;
+    const __nv_bfloat16 *px = x + img * hw * c;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float s = 0.f;
+        for (int i = 0; i < hw; ++i) s += __bfloat162float(px[(long long)i * c + ch]);
+        y[img * ldy + ch] = s / (float)hw;
+    }
+}
+
+}  // namespace
+
+extern "C" int ewvit_mwt_head_fwd(const float *hf, int n, int hin, int win, int hout, int wout, const float *w,
+                                  const float *scale, const float *shift, void *y, void *stream) {
+    EWVIT_REQUIRE(n >= 0 && hin > 0 && win > 0 && hout > 0 && wout > 0, EWVIT_ERR_INVALID_ARG, "ewvit_mwt_head_fwd: bad sizes");
+    if (n == 0) return EWVIT_OK;
+    EWVIT_REQUIRE(hf && w && scale && shift && y, EWVIT_ERR_INVALID_ARG, "ewvit_mwt_head_fwd: NULL pointer");
+    EWVIT_REQUIRE(ewvit_aligned16(y), EWVIT_ERR_INVALID_ARG, "ewvit_mwt_head_fwd: y must be 16-byte aligned");
+    EWVIT_REQUIRE(n <= 65535, EWVIT_ERR_UNSUPPORTED, "ewvit_mwt_head_fwd: n=%d > 65535 frames per call", n);
+    int rc = ewvit_check_device();
+    if (rc != EWVIT_OK) return rc;
+    HeadParams p;
+    p.hf = hf; p.w = w; p.scale = scale; p.shift = shift; p.y = static_cast<__nv_bfloat16 *>(y);
+    p.n = n; p.hin = hin; p.win = win; p.hout = hout; p.wout = wout;
+    p.ry = (float)hin / (float)hout;
+    p.rx = (float)win / (float)wout;
+    const int tiles = ((hout + kTile - 1) / kTile) * ((wout + kTile - 1) / kTile);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    EWVIT_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(mwt_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    mwt_head_kernel<<<dim3(tiles, n), kHeadThreads, kHeadSmem, (cudaStream_t)stream>>>(p);
+    EWVIT_LAUNCH_OK();
+    return EWVIT_OK;
+}
+
+extern "C" int ewvit_maxpool2x2_nhwc_bf16(const void *x, int64_t n, int h, int w, int c, void *y, void *stream) {
+    EWVIT_REQUIRE(n >= 0 && h > 0 && w > 0 && c > 0, EWVIT_ERR_INVALID_ARG, "ewvit_maxpool2x2_nhwc_bf16: bad sizes");
+    if (n == 0) return EWVIT_OK;
+    EWVIT_REQUIRE(x && y && ewvit_aligned16(x) && ewvit_aligned16(y), EWVIT_ERR_INVALID_ARG,
+                  "ewvit_maxpool2x2_nhwc_bf16: NULL or misaligned pointer");
+    EWVIT_REQUIRE(h % 2 == 0 && w % 2 == 0 && c % 8 == 0, EWVIT_ERR_UNSUPPORTED,
+                  "ewvit_maxpool2x2_nhwc_bf16: needs even h, w and c %% 8 == 0");
+    int rc = ewvit_check_device();
+    if (rc != EWVIT_OK) return rc;
+    const long long total = n * (h / 2) * (w / 2) * (c / 8);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)ewvit_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    maxpool2x2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const __nv_bfloat16 *>(x), static_cast<__nv_bfloat16 *>(y), n, h, w, c);
+    EWVIT_LAUNCH_OK();
+    return EWVIT_OK;
+}
+
+extern "C" int ewvit_gap_nhwc_bf16(const void *x, int64_t n, int hw, int c, float *y, int64_t ldy, void *stream) {
+    EWVIT_REQUIRE(n >= 0 && hw > 0 && c > 0 && ldy >= c, EWVIT_ERR_INVALID_ARG, "ewvit_gap_nhwc_bf16: bad sizes");
+    if (n == 0) return EWVIT_OK;
+    EWVIT_REQUIRE(x && y, EWVIT_ERR_INVALID_ARG, "ewvit_gap_nhwc_bf16: NULL pointer");
+    int rc = ewvit_check_device();
+    if (rc != EWVIT_OK) return rc;
+    gap_kernel<<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16 *>(x), y, hw, c, ldy);
+    EWVIT_LAUNCH_OK();
+    return EWVIT_OK;
+}

@@ -4,6 +4,8 @@ import os
 import threading
 from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
 
+P = c_void_p
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LOCK = threading.Lock()
 _LIB = None
@@ -28,6 +30,15 @@ SIGNATURES = {
                                   c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "ewvit_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ewvit_mwt_head_fwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "ewvit_maxpool2x2_nhwc_bf16": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
+    "ewvit_gap_nhwc_bf16": (c_int, [P, c_int64, c_int, c_int, P, c_int64, P]),
+    "ewvit_vit_assemble": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, P]),
+    "ewvit_layernorm_bf16": (c_int, [P, c_int64, P, P, c_float, P, c_int64, c_int64, c_int, P]),
+    "ewvit_vit_attention": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
+    "ewvit_dama_wpack_floats": (c_int64, [c_int, c_int]),
+    "ewvit_dama_tail_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, P, c_float, P, P, P, P]),
+    "ewvit_video_head_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P, P, P, P, P, c_int, P, P]),
 }
 
 

@@ -1,0 +1,347 @@
+"""Host-side runners of the native EWViT forward path (eval mode, bf16 tensor-core math, fp32 glue).
+
+Each runner owns (a) weights re-laid-out for the kernels (folded BatchNorm, tap-major bf16 conv weights,
+transposed DAMA matrices) and (b) per-batch-size workspaces, and strings the C-ABI kernels of
+``libewvit.so`` together.  PyTorch is used for memory, streams and the third-party EfficientNet backbone
+(cuDNN, bf16 channels-last) only.  Nothing here runs on the CPU and nothing falls back.
+
+Reference call stacks being replaced: ``MWT.forward`` (network/mwt.py:92-119), ``EfficientViT.forward``
+(network/sfe.py:145-173), ``DAMA._process_frame``/``DAMA.forward`` (network/dama.py:130-206) and the
+``dynamic`` branch of ``DeepfakeDetector.forward`` (network/model.py:83-99).
+"""
+import copy
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import EwvitError
+
+BN_EPS = 1e-5
+LN_EPS = 1e-5
+MACRO_BATCH = 512          # frames per pass: bounds the MWT workspace (~17 MB / frame)
+
+
+def _fold_bn(sd, conv, bn, eps=BN_EPS):
+    """conv bias + eval BatchNorm -> per-channel (scale, shift) applied to the bias-free conv output."""
+    scale = sd[bn + "weight"].float() / torch.sqrt(sd[bn + "running_var"].float() + eps)
+    shift = sd[bn + "bias"].float() + (sd[conv + "bias"].float() - sd[bn + "running_mean"].float()) * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def _conv_w_tapmajor(w, cin_pad=None):
+    """[cout, cin, 3, 3] -> bf16 [cout, 3, 3, cin_pad] (k = (ky*3+kx)*cin_pad + c)."""
+    cout, cin = w.shape[:2]
+    cin_pad = cin_pad or cin
+    out = torch.zeros((cout, 3, 3, cin_pad), dtype=torch.bfloat16, device=w.device)
+    out[..., :cin] = w.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return out.contiguous()
+
+
+def _sub(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+# ------------------------------------------------------------------------------------------ MWT
+class MwtRunner:
+    """Native ``MWT.forward`` (levels = 3, in_channels = 3).  ``sd`` holds the module's own keys
+    (``hf_conv.seperate.0.0.weight`` ...) as CUDA tensors."""
+
+    def __init__(self, sd, dim=128, levels=3, in_channels=3):
+        if in_channels != 3:
+            raise EwvitError("native MWT supports in_channels=3 (9 high-frequency planes) only")
+        if dim % 128 != 0:
+            raise EwvitError(f"native MWT needs dama_dim to be a multiple of 128 (got {dim})")
+        if levels != 3:
+            raise EwvitError("native MWT implements the reference's 3-level decomposition (model.py:35) only")
+        self.dim, self.levels = dim, levels
+        dev = sd["freq_conv.0.weight"].device
+        self.device = dev
+        # hf_conv.seperate: three Conv2d(3,18)+BN, stacked
+        self.head_w = torch.stack([sd[f"hf_conv.seperate.{i}.0.weight"].float() for i in range(3)]).contiguous()
+        sc, sh = zip(*[_fold_bn(sd, f"hf_conv.seperate.{i}.0.", f"hf_conv.seperate.{i}.1.") for i in range(3)])
+        self.head_scale, self.head_shift = torch.cat(sc).contiguous(), torch.cat(sh).contiguous()
+        self.fus_w = _conv_w_tapmajor(sd["hf_conv.fusion.0.weight"], 64)
+        self.fus_scale, self.fus_shift = _fold_bn(sd, "hf_conv.fusion.0.", "hf_conv.fusion.1.")
+        self.ms_w = _conv_w_tapmajor(sd["multiscale_fusion.0.weight"])
+        self.ms_scale, self.ms_shift = _fold_bn(sd, "multiscale_fusion.0.", "multiscale_fusion.1.")
+        self.fc_w = _conv_w_tapmajor(sd["freq_conv.0.weight"])
+        self.fc_scale, self.fc_shift = _fold_bn(sd, "freq_conv.0.", "freq_conv.1.")
+        self.fp_w = _conv_w_tapmajor(sd["freq_pool.1.weight"])
+        self.fp_scale, self.fp_shift = _fold_bn(sd, "freq_pool.1.", "freq_pool.2.")
+        self._ws = {}
+
+    def _workspace(self, n, h, w):
+        key = (n, h, w)
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) > 4:
+                self._ws.clear()
+            dev, bf = self.device, torch.bfloat16
+            h1, w1, d = h // 2, w // 2, self.dim
+            h2, w2 = (h1 - 1) // 2 + 1, (w1 - 1) // 2 + 1          # freq_conv, stride 2
+            h4, w4 = (h2 // 2 - 1) // 2 + 1, (w2 // 2 - 1) // 2 + 1  # maxpool then stride-2 conv
+            ws = {
+                "hf": [torch.empty((n, 3, 3, h >> l, w >> l), dtype=torch.float32, device=dev) for l in (1, 2, 3)],
+                "head": torch.zeros((n, h1 + 2, w1 + 2, 64), dtype=bf, device=dev),      # zero border, kept zero
+                "cat": torch.empty((n, h1 + 2, w1 + 2, 3 * d), dtype=bf, device=dev),
+                "ms": torch.empty((n, h1 + 2, w1 + 2, d), dtype=bf, device=dev),
+                "fc": torch.empty((n, h2, w2, d), dtype=bf, device=dev),
+                "mp": torch.empty((n, h2 // 2, w2 // 2, d), dtype=bf, device=dev),
+                "pc": torch.empty((n, h4, w4, d), dtype=bf, device=dev),
+            }
+            self._ws[key] = ws
+        return ws
+
+    def forward(self, frames, out=None):
+        """frames [n,3,H,W] fp32 CUDA (H, W multiples of 8) -> [n, dim] fp32."""
+        n, c, h, w = frames.shape
+        if c != 3 or h % 8 or w % 8:
+            raise EwvitError(f"native MWT needs [n,3,H,W] with H,W multiples of 8 (got {tuple(frames.shape)})")
+        ws = self._workspace(n, h, w)
+        h1, w1, d = h // 2, w // 2, self.dim
+        hf = ws["hf"]
+        ops.dwt3_haar(frames, out={"hf1": hf[0], "hf2": hf[1], "hf3": hf[2]}, want=("hf1", "hf2", "hf3"))
+        for lvl in range(3):
+            ops.mwt_head(hf[lvl].view(n, 9, h >> (lvl + 1), w >> (lvl + 1)), self.head_w, self.head_scale,
+                         self.head_shift, ws["head"], h1, w1)
+            ops.conv3x3_bf16(ws["head"], self.fus_w, n, h1, w1, 1, True, self.fus_scale, self.fus_shift, True,
+                             ws["cat"], lvl * d, True)
+        ops.conv3x3_bf16(ws["cat"], self.ms_w, n, h1, w1, 1, True, self.ms_scale, self.ms_shift, True, ws["ms"], 0, True)
+        ops.conv3x3_bf16(ws["ms"], self.fc_w, n, h1, w1, 2, True, self.fc_scale, self.fc_shift, True, ws["fc"], 0, False)
+        ops.maxpool2x2(ws["fc"], ws["mp"])
+        hp, wp = ws["mp"].shape[1:3]
+        ops.conv3x3_bf16(ws["mp"], self.fp_w, n, hp, wp, 2, False, self.fp_scale, self.fp_shift, True, ws["pc"], 0, False)
+        return ops.gap(ws["pc"], out)
+
+
+# ------------------------------------------------------------------------------------------ SFE
+def fused_bf16_backbone(features: nn.Module, device):
+    """Inference copy of an EfficientNet feature extractor: BatchNorm folded into the preceding conv,
+    bf16, channels-last (so the [N,1280,7,7] output is NHWC in memory and the reference's
+    ``rearrange 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)'`` at sfe.py:153 is a free view)."""
+    net = copy.deepcopy(features).eval().float()
+
+    def fuse(mod):
+        for name, child in list(mod.named_children()):
+            fuse(child)
+        if isinstance(mod, nn.Sequential) and len(mod) >= 2 and isinstance(mod[0], nn.Conv2d) and isinstance(mod[1], nn.BatchNorm2d):
+            mod[0] = torch.nn.utils.fuse_conv_bn_eval(mod[0], mod[1])
+            mod[1] = nn.Identity()
+
+    fuse(net)
+    return net.to(device=device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+
+
+class SfeRunner:
+    """Native ``EfficientViT.forward`` after the backbone; ``backbone`` maps fp32 frames to the bf16 NHWC
+    feature map.  ``sd`` holds the module's own keys (``patch_to_embedding.weight`` ...)."""
+
+    def __init__(self, sd, cfg, backbone, output_mode="feature_map"):
+        m = cfg["model"]
+        self.dim, self.depth, self.heads, self.dim_head = m["dim"], m["depth"], m["heads"], m["dim-head"]
+        self.mlp_dim, self.emb_dim = m["mlp-dim"], m["emb-dim"]
+        self.output_mode = output_mode
+        self.backbone = backbone
+        bf = torch.bfloat16
+        f32 = lambda k: sd[k].float().contiguous()
+        self.patch_w = sd["patch_to_embedding.weight"].to(bf).contiguous()
+        self.patch_b = f32("patch_to_embedding.bias")
+        self.cls = f32("cls_token").reshape(-1)
+        self.pos = f32("pos_embedding").reshape(-1, self.dim)
+        self.layers = []
+        for l in range(self.depth):
+            q = f"transformer.layers.{l}."
+            self.layers.append({
+                "ln1": (f32(q + "0.norm.weight"), f32(q + "0.norm.bias")),
+                "qkv": sd[q + "0.fn.to_qkv.weight"].to(bf).contiguous(),
+                "out_w": sd[q + "0.fn.to_out.0.weight"].to(bf).contiguous(), "out_b": f32(q + "0.fn.to_out.0.bias"),
+                "ln2": (f32(q + "1.norm.weight"), f32(q + "1.norm.bias")),
+                "ff1_w": sd[q + "1.fn.net.0.weight"].to(bf).contiguous(), "ff1_b": f32(q + "1.fn.net.0.bias"),
+                "ff2_w": sd[q + "1.fn.net.3.weight"].to(bf).contiguous(), "ff2_b": f32(q + "1.fn.net.3.bias"),
+            })
+        for w in (self.patch_w, *[l[k] for l in self.layers for k in ("qkv", "out_w", "ff1_w", "ff2_w")]):
+            if w.shape[0] % 128 or w.shape[1] % 64:
+                raise EwvitError("native SFE needs every Linear to have out %128 == 0 and in %64 == 0 "
+                                 f"(architecture.yaml gives {tuple(w.shape)})")
+        if output_mode == "cls":
+            self.h1_w = sd["mlp_head.0.weight"].to(bf).contiguous()
+            self.h1_b = f32("mlp_head.0.bias")
+            w2 = sd["mlp_head.2.weight"]
+            self.num_classes = w2.shape[0]
+            self.h2_w = torch.zeros((128, w2.shape[1]), dtype=bf, device=w2.device)
+            self.h2_w[: w2.shape[0]] = w2.to(bf)
+            self.h2_b = torch.zeros(128, dtype=torch.float32, device=w2.device)
+            self.h2_b[: w2.shape[0]] = sd["mlp_head.2.bias"].float()
+        else:
+            fw = sd["feat_map.0.weight"]
+            self.feat_dim = fw.shape[0]
+            pad = (-fw.shape[0]) % 128
+            self.fm_w = torch.cat([fw.to(bf), torch.zeros((pad, fw.shape[1]), dtype=bf, device=fw.device)]).contiguous()
+            self.fm_b = torch.cat([sd["feat_map.0.bias"].float(), torch.zeros(pad, device=fw.device)]).contiguous()
+        self._ws = {}
+
+    def _workspace(self, n, dev):
+        ws = self._ws.get(n)
+        if ws is None:
+            if len(self._ws) > 4:
+                self._ws.clear()
+            f32, bf = torch.float32, torch.bfloat16
+            inner = self.heads * self.dim_head
+            kblocks = self.patch_w.shape[1] // 64
+            splits = max(1, min(kblocks, 148 // max(1, math.ceil(n / 128) * (self.dim // 128))))
+            ws = {
+                "splits": splits,
+                "ws": torch.empty((splits, n, self.dim), dtype=f32, device=dev) if splits > 1 else None,
+                "emb": torch.empty((n, self.dim), dtype=f32, device=dev),
+                "x": [torch.empty((2 * n, self.dim), dtype=f32, device=dev) for _ in range(2)],
+                "xn": torch.empty((2 * n, self.dim), dtype=bf, device=dev),
+                "qkv": torch.empty((2 * n, 3 * inner), dtype=f32, device=dev),
+                "att": torch.empty((2 * n, inner), dtype=bf, device=dev),
+                "hid": torch.empty((2 * n, self.mlp_dim), dtype=bf, device=dev),
+                "tok": torch.empty((n, self.dim), dtype=bf, device=dev),
+            }
+            self._ws[n] = ws
+        return ws
+
+    def head(self, feat_nhwc, pos_index, out=None):
+        """feat_nhwc: bf16 [n, ph*pw*channels] (NHWC flatten of the backbone map); pos_index int32 [n]."""
+        n = feat_nhwc.shape[0]
+        ws = self._workspace(n, feat_nhwc.device)
+        ops.linear_bf16(feat_nhwc, self.patch_w, shift=self.patch_b, out=ws["emb"], splits=ws["splits"], workspace=ws["ws"])
+        x, y = ws["x"]
+        ops.vit_assemble(ws["emb"], self.cls, self.pos, pos_index, out=x)
+        for L in self.layers:
+            ops.layernorm_bf16(x, *L["ln1"], eps=LN_EPS, out=ws["xn"])
+            ops.linear_bf16(ws["xn"], L["qkv"], out=ws["qkv"])
+            ops.vit_attention(ws["qkv"], n, 2, self.heads, self.dim_head, out=ws["att"])
+            ops.linear_bf16(ws["att"], L["out_w"], shift=L["out_b"], residual=x, out=y)
+            ops.layernorm_bf16(y, *L["ln2"], eps=LN_EPS, out=ws["xn"])
+            ops.linear_bf16(ws["xn"], L["ff1_w"], shift=L["ff1_b"], act="gelu", out=ws["hid"])
+            ops.linear_bf16(ws["hid"], L["ff2_w"], shift=L["ff2_b"], residual=y, out=x)
+        d = self.dim
+        if self.output_mode == "cls":      # token 0 -> mlp_head (sfe.py:163-166)
+            ops.layernorm_bf16(x, None, None, out=ws["tok"], rows=n, ldx=2 * d, d=d)
+            hid = ops.linear_bf16(ws["tok"], self.h1_w, shift=self.h1_b, act="relu", out_dtype=torch.bfloat16)
+            res = ops.linear_bf16(hid, self.h2_w, shift=self.h2_b)
+            return res[:, : self.num_classes].contiguous()
+        # token 1 -> feat_map Linear + ReLU (sfe.py:168-173)
+        ops.layernorm_bf16(x[1], None, None, out=ws["tok"], rows=n, ldx=2 * d, d=d)   # rows 1, 3, 5, ...
+        res = ops.linear_bf16(ws["tok"], self.fm_w, shift=self.fm_b, act="relu", out=out if self.fm_w.shape[0] == self.feat_dim else None)
+        return res if res.shape[1] == self.feat_dim else res[:, : self.feat_dim].contiguous()
+
+    def features(self, frames):
+        """fp32 frames [n,3,H,W] -> bf16 [n, 62720] NHWC-flattened backbone features."""
+        x = frames.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        f = self.backbone(x)                                     # [n, C, ph, pw], channels-last memory
+        n = f.shape[0]
+        return f.permute(0, 2, 3, 1).reshape(n, -1)              # view when channels-last
+
+    def forward(self, frames, pos_index, out=None):
+        feat = self.features(frames)
+        if not feat.is_contiguous():
+            feat = feat.contiguous()
+        return self.head(feat, pos_index, out)
+
+
+# ------------------------------------------------------------------------------------------ DAMA
+def pack_dama_weights(sd, dim, depth=2):
+    """Flatten the cross-attention / gate weights into the layout of ``ewvit_dama_tail_fwd`` (include/ewvit.h)."""
+    parts = []
+    f = lambda k: sd[k].float()
+    for l in range(depth):
+        for ln, att in ((0, 1), (2, 3)):
+            q = f"cross_att.layers.{l}."
+            parts += [f(f"{q}{ln}.weight"), f(f"{q}{ln}.bias"), f(f"{q}{att}.to_q.weight").t(), f(f"{q}{att}.to_kv.weight").t(),
+                      f(f"{q}{att}.to_out.0.weight").t(), f(f"{q}{att}.to_out.0.bias")]
+    centre = f("fusion_gate.0.weight")[:, :, 1, 1]              # [dim, 2*dim]: only the centre tap is live on a 1x1 map
+    scale, shift = _fold_bn(sd, "fusion_gate.0.", "fusion_gate.1.")
+    parts += [centre.t(), scale, shift, f("gate_net.2.weight").t(), f("gate_net.2.bias"), f("gate_net.5.weight"), f("gate_net.5.bias")]
+    pack = torch.cat([p.contiguous().reshape(-1) for p in parts]).contiguous()
+    assert pack.numel() == ops.dama_wpack_floats(dim, depth)
+    return pack
+
+
+def chunk_pos_index(b, k, batch_size):
+    """Position of every frame inside its reference chunk: ``DAMA.forward`` feeds ``x[:, s:e].flatten(0,1)``
+    (dama.py:179-186) and ``EfficientViT.forward`` adds ``pos_embedding[0:N]`` along that flattened axis
+    (sfe.py:158-159), so frame (b, k) of a chunk of length L gets row ``b*L + (k - s)``.  Raises like the
+    reference's broadcast when a chunk holds more than ``emb-dim`` frames."""
+    idx = torch.empty((b, k), dtype=torch.int32)
+    for s in range(0, k, batch_size):
+        e = min(s + batch_size, k)
+        length = e - s
+        idx[:, s:e] = torch.arange(b, dtype=torch.int32).view(b, 1) * length + torch.arange(length, dtype=torch.int32).view(1, length)
+    return idx.reshape(-1)
+
+
+def check_chunk_limit(b, k, batch_size, emb_dim):
+    n = b * min(batch_size, k)
+    if n > emb_dim:
+        raise RuntimeError(f"The size of tensor a ({n}) must match the size of tensor b ({emb_dim}) at "
+                           "non-singleton dimension 0")
+
+
+class DamaRunner:
+    """Native ``DAMA.forward`` (dynamic mode).  ``sd`` holds the DAMA module's own keys."""
+
+    def __init__(self, sd, cfg, backbone, dim=128, heads=4, levels=3, depth=2):
+        self.dim, self.heads, self.depth = dim, heads, depth
+        self.cfg = cfg
+        self.sfe = SfeRunner(_sub(sd, "sfe."), cfg, backbone)
+        self.mwt = MwtRunner(_sub(sd, "mwt."), dim=dim, levels=levels)
+        self.wpack = pack_dama_weights(sd, dim, depth)
+        self._pos_cache = {}
+        self.side_stream = None
+
+    def pos_index(self, b, k, batch_size, device):
+        key = (b, k, batch_size, str(device))
+        t = self._pos_cache.get(key)
+        if t is None:
+            if len(self._pos_cache) > 16:
+                self._pos_cache.clear()
+            t = chunk_pos_index(b, k, batch_size).to(device)
+            self._pos_cache[key] = t
+        return t
+
+    def process_frames(self, frames, pos_index):
+        """frames [n,3,H,W] -> (fused, space, freq) each [n, dim] fp32 (``_process_frame``, dama.py:130-169)."""
+        space = self.sfe.forward(frames, pos_index)
+        freq = self.mwt.forward(frames)
+        return ops.dama_tail(space, freq, self.wpack, self.heads, self.depth, LN_EPS)
+
+    def forward_frames(self, x, batch_size):
+        """x [B,K,3,H,W] fp32 CUDA -> per-frame (fused, space, freq) [B*K, dim] in (b, k) order."""
+        b, k = x.shape[:2]
+        check_chunk_limit(b, k, batch_size, self.sfe.emb_dim)
+        frames = x.reshape(b * k, *x.shape[2:])
+        if not frames.is_contiguous():
+            frames = frames.contiguous()
+        pos = self.pos_index(b, k, batch_size, x.device)
+        n = b * k
+        if n <= MACRO_BATCH:
+            return self.process_frames(frames, pos)
+        outs = [torch.empty((n, self.dim), dtype=torch.float32, device=x.device) for _ in range(3)]
+        for s in range(0, n, MACRO_BATCH):
+            e = min(s + MACRO_BATCH, n)
+            part = self.process_frames(frames[s:e], pos[s:e])
+            for o, p in zip(outs, part):
+                o[s:e].copy_(p)
+        return tuple(outs)
+
+
+class DetectorRunner:
+    """Native ``DeepfakeDetector.forward(x, batch_size, 'dynamic')`` (model.py:83-99)."""
+
+    def __init__(self, sd, cfg, backbone, dim=128):
+        self.dama = DamaRunner(_sub(sd, "dama."), cfg, backbone, dim=dim)
+        f = lambda k: sd[k].float().contiguous()
+        self.classifier = (f("classifier.0.weight"), f("classifier.0.bias"), f("classifier.3.weight").reshape(-1).contiguous(),
+                           f("classifier.3.bias"))
+
+    def forward(self, x, batch_size):
+        b, k = x.shape[:2]
+        fused, space, freq = self.dama.forward_frames(x, batch_size)
+        mf, ms, mq, logits = ops.video_head(fused, space, freq, b, k, self.classifier)
+        return {"logits": logits, "fused": mf, "space": ms, "freq": mq}

@@ -139,3 +139,134 @@ def conv3x3_bf16(x, w, n, h, wd, stride, in_padded, scale, shift, relu, y, y_cof
                                         _ptr(scale), _ptr(shift), int(relu), y.data_ptr(), ldc, y_coff,
                                         int(out_padded), int(force_tiled), _stream()), "ewvit_conv3x3_bf16")
     return y
+
+
+def _check_f32(t, name):
+    _require_cuda(t, name)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise EwvitError(f"{name} must be a contiguous fp32 CUDA tensor")
+
+
+def mwt_head(hf, w, scale, shift, y, hout, wout):
+    """hf [n,9,hin,win] fp32 -> y [n,hout+2,wout+2,64] bf16 (interior written). See include/ewvit.h."""
+    for t, nm in ((hf, "hf"), (w, "w"), (scale, "scale"), (shift, "shift")):
+        _check_f32(t, nm)
+    _check_bf16(y, "y")
+    n, c9, hin, win = hf.shape
+    if c9 != 9 or w.numel() != 3 * 18 * 27 or scale.numel() != 54 or shift.numel() != 54:
+        raise EwvitError("mwt_head: expects 9 high-frequency channels (in_channels=3) and 3x18x27 weights")
+    if y.numel() != n * (hout + 2) * (wout + 2) * 64:
+        raise EwvitError("mwt_head: bad y size")
+    with torch.cuda.device(hf.device):
+        check(load().ewvit_mwt_head_fwd(hf.data_ptr(), n, hin, win, hout, wout, w.data_ptr(), scale.data_ptr(),
+                                        shift.data_ptr(), y.data_ptr(), _stream()), "ewvit_mwt_head_fwd")
+    return y
+
+
+def maxpool2x2(x, y=None):
+    """NHWC bf16 [n,h,w,c] -> [n,h/2,w/2,c]."""
+    _check_bf16(x, "x", 4)
+    n, h, w, c = x.shape
+    if y is None:
+        y = torch.empty((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().ewvit_maxpool2x2_nhwc_bf16(x.data_ptr(), n, h, w, c, y.data_ptr(), _stream()),
+              "ewvit_maxpool2x2_nhwc_bf16")
+    return y
+
+
+def gap(x, y=None):
+    """NHWC bf16 [n,h,w,c] -> fp32 [n,c] mean over pixels."""
+    _check_bf16(x, "x", 4)
+    n, h, w, c = x.shape
+    if y is None:
+        y = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().ewvit_gap_nhwc_bf16(x.data_ptr(), n, h * w, c, y.data_ptr(), y.stride(0), _stream()),
+              "ewvit_gap_nhwc_bf16")
+    return y
+
+
+def vit_assemble(emb, cls, pos, pos_index, out=None):
+    _check_f32(emb, "emb")
+    n, d = emb.shape
+    if pos_index.dtype != torch.int32 or pos_index.numel() != n or not pos_index.is_cuda:
+        raise EwvitError("vit_assemble: pos_index must be an int32 CUDA tensor with one entry per frame")
+    cls, pos = cls.reshape(-1), pos.reshape(-1, d)
+    _check_f32(cls, "cls")
+    _check_f32(pos, "pos")
+    if out is None:
+        out = torch.empty((n * 2, d), dtype=torch.float32, device=emb.device)
+    with torch.cuda.device(emb.device):
+        check(load().ewvit_vit_assemble(emb.data_ptr(), cls.data_ptr(), pos.data_ptr(), pos_index.data_ptr(), n, d,
+                                        pos.shape[0], out.data_ptr(), _stream()), "ewvit_vit_assemble")
+    return out
+
+
+def layernorm_bf16(x, gamma, beta, eps=1e-5, out=None, rows=None, ldx=None, d=None):
+    """fp32 rows -> bf16 LayerNorm (or plain cast when gamma is None). x may be a strided row view:
+    pass rows/ldx/d explicitly with x the tensor whose data_ptr is the first row."""
+    _require_cuda(x, "x")
+    if x.dtype != torch.float32:
+        raise EwvitError("layernorm_bf16: x must be fp32")
+    if rows is None:
+        rows, d = x.shape
+        ldx = x.stride(0)
+    if out is None:
+        out = torch.empty((rows, d), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().ewvit_layernorm_bf16(x.data_ptr(), ldx, _ptr(gamma), _ptr(beta), eps, out.data_ptr(),
+                                          out.stride(0), rows, d, _stream()), "ewvit_layernorm_bf16")
+    return out
+
+
+def vit_attention(qkv, n, tokens, heads, dim_head, out=None):
+    _check_f32(qkv, "qkv")
+    if out is None:
+        out = torch.empty((n * tokens, heads * dim_head), dtype=torch.bfloat16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(load().ewvit_vit_attention(qkv.data_ptr(), n, tokens, heads, dim_head, out.data_ptr(), _stream()),
+              "ewvit_vit_attention")
+    return out
+
+
+def dama_wpack_floats(d, depth):
+    return int(load().ewvit_dama_wpack_floats(d, depth))
+
+
+def dama_tail(space_in, freq_in, wpack, heads, depth, ln_eps=1e-5, out=None):
+    _check_f32(space_in, "space_in")
+    _check_f32(freq_in, "freq_in")
+    _check_f32(wpack, "wpack")
+    n, d = space_in.shape
+    if wpack.numel() != dama_wpack_floats(d, depth):
+        raise EwvitError("dama_tail: wpack has the wrong size")
+    if out is None:
+        out = tuple(torch.empty((n, d), dtype=torch.float32, device=space_in.device) for _ in range(3))
+    fused, space, freq = out
+    with torch.cuda.device(space_in.device):
+        check(load().ewvit_dama_tail_fwd(space_in.data_ptr(), freq_in.data_ptr(), n, d, heads, depth, wpack.data_ptr(),
+                                         ln_eps, fused.data_ptr(), space.data_ptr(), freq.data_ptr(), _stream()),
+              "ewvit_dama_tail_fwd")
+    return fused, space, freq
+
+
+def video_head(fused, space, freq, videos, k, classifier=None):
+    """Per-video means (+ classifier logits when classifier=(w1[hc,d], b1[hc], w2[hc], b2[1]))."""
+    _check_f32(fused, "fused")
+    d = fused.shape[-1]
+    dev = fused.device
+    mf = torch.empty((videos, d), dtype=torch.float32, device=dev)
+    ms = torch.empty_like(mf) if space is not None else None
+    mq = torch.empty_like(mf) if freq is not None else None
+    logits = torch.empty((videos, 1), dtype=torch.float32, device=dev) if classifier is not None else None
+    cw1 = cb1 = cw2 = cb2 = None
+    hc = 0
+    if classifier is not None:
+        cw1, cb1, cw2, cb2 = classifier
+        hc = cw1.shape[0]
+    with torch.cuda.device(dev):
+        check(load().ewvit_video_head_fwd(fused.data_ptr(), _ptr(space), _ptr(freq), videos, k, d, mf.data_ptr(),
+                                          _ptr(ms), _ptr(mq), _ptr(cw1), _ptr(cb1), _ptr(cw2), _ptr(cb2), hc,
+                                          _ptr(logits), _stream()), "ewvit_video_head_fwd")
+    return mf, ms, mq, logits

@@ -123,6 +123,81 @@ EWVIT_API int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, int
                                  int stride, int in_padded, const float *scale, const float *shift, int relu,
                                  void *y, int y_ldc, int y_coff, int out_padded, int force_tiled, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * MWT glue  (rows a-3, a-4)
+ * ------------------------------------------------------------------------------------------- */
+
+/* High-frequency head of one wavelet level: reference network/mwt.py:77-86 --
+ * `hf[0].reshape(B, 3C, h, w)` (colour-major), `F.interpolate(..., mode='bilinear')` to the level-1 grid
+ * (align_corners=False; identity when hin == hout), then the three per-colour Conv2d(3->18,3x3,p1)+BN+ReLU
+ * of hf_conv['seperate'] and their channel concat.
+ *   hf    [n, 9, hin, win] fp32   (= yh of ewvit_dwt*_haar_fwd viewed as [n, 3*3, hin, win])
+ *   w     [3, 18, 3, 3, 3] fp32   (group, out channel, in channel, ky, kx) = the three conv weights stacked
+ *   scale [54], shift [54] fp32   folded conv bias + eval BatchNorm per concatenated channel
+ *   y     [n, hout+2, wout+2, 64] bf16 padded-flat NHWC; only the interior pixels are written (channels 54..63
+ *         as zeros); the one-pixel border must be zero (zero the buffer once). */
+EWVIT_API int ewvit_mwt_head_fwd(const float *hf, int n, int hin, int win, int hout, int wout, const float *w,
+                                 const float *scale, const float *shift, void *y, void *stream);
+
+/* nn.MaxPool2d(2, 2) on NHWC bf16 (freq_pool[0], mwt.py:39): x [n,h,w,c] -> y [n,h/2,w/2,c]. */
+EWVIT_API int ewvit_maxpool2x2_nhwc_bf16(const void *x, int64_t n, int h, int w, int c, void *y, void *stream);
+
+/* nn.AdaptiveAvgPool2d(1) on NHWC bf16 (freq_pool[4], mwt.py:43): x [n, hw, c] -> y [n, ldy] fp32. */
+EWVIT_API int ewvit_gap_nhwc_bf16(const void *x, int64_t n, int hw, int c, float *y, int64_t ldy, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Efficient-ViT token glue  (row a-5)
+ * ------------------------------------------------------------------------------------------- */
+
+/* reference network/sfe.py:156-159: x = cat(cls_token, patch_embedding) + pos_embedding[0:N], with the
+ * position resolved per frame by the caller (pos_index[f] = position of frame f inside its reference chunk).
+ *   emb [n, d] fp32 (patch_to_embedding output incl. bias)   cls [d]   pos [pos_rows, d]   pos_index [n] int32
+ *   x   [n, 2, d] fp32 */
+EWVIT_API int ewvit_vit_assemble(const float *emb, const float *cls, const float *pos, const int *pos_index,
+                                 int64_t n, int d, int pos_rows, float *x, void *stream);
+
+/* nn.LayerNorm (sfe.py:23, dama.py:63-66) on fp32 rows, bf16 result ready to be a GEMM operand.
+ * gamma == beta == NULL: plain strided fp32 -> bf16 cast (used to pick token 1 for feat_map, sfe.py:171).
+ *   x [rows, ldx] fp32 -> y [rows, ldy] bf16 over the first d columns */
+EWVIT_API int ewvit_layernorm_bf16(const float *x, int64_t ldx, const float *gamma, const float *beta, float eps,
+                                   void *y, int64_t ldy, int64_t rows, int d, void *stream);
+
+/* Attention core of sfe.py:58-69 for `tokens` tokens per frame (2 at the shipped config):
+ *   qkv [n*tokens, 3*heads*dim_head] fp32 (q | k | v, head-major) -> out [n*tokens, heads*dim_head] bf16 */
+EWVIT_API int ewvit_vit_attention(const float *qkv, int64_t n, int tokens, int heads, int dim_head, void *out,
+                                  void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DAMA fusion tail  (rows a-7 .. a-10)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Number of floats in the packed weight buffer of ewvit_dama_tail_fwd. */
+EWVIT_API int64_t ewvit_dama_wpack_floats(int d, int depth);
+
+/* reference network/dama.py:143-169 (`DAMA._process_frame` after the two branches): BidirectionalCrossTransformer
+ * (depth x {space attends freq, freq attends space}, kv_include_self=True => 1 query x 2 keys), fusion_gate
+ * (centre tap of the 3x3 conv on the 1x1 map + eval BatchNorm + ReLU), gate_net (Linear-ReLU-Linear-softmax(3)),
+ * weighted sum.  fp32 throughout.
+ *   space_in, freq_in [n, d]                 fused, space, freq [n, d] (outputs)
+ *   wpack: fp32, all matrices TRANSPOSED to [in, out]:
+ *     for l in 0..depth-1, for dir in (space<-freq, freq<-space):
+ *        ln_w[d] ln_b[d] to_q^T[d,d] to_kv^T[d,2d] to_out^T[d,d] to_out_bias[d]
+ *     fusion_gate centre tap^T [2d,d], folded scale[d], folded shift[d],
+ *     gate_net.2^T [2d, d/2], gate_net.2 bias [d/2], gate_net.5 weight [3, d/2] (not transposed), gate_net.5 bias [3] */
+EWVIT_API int ewvit_dama_tail_fwd(const float *space_in, const float *freq_in, int64_t n, int d, int heads, int depth,
+                                  const float *wpack, float ln_eps, float *fused, float *space, float *freq,
+                                  void *stream);
+
+/* reference network/dama.py:188-199 (per-video mean over the k frames of each video; frames of a video are
+ * consecutive rows) and network/model.py:62-68,92 (classifier Linear(d->hc)+ReLU+Linear(hc->1), eval mode).
+ * space/freq (and their means) may be NULL; cw1 == NULL skips the classifier.
+ *   fused/space/freq [videos*k, d] -> mean_* [videos, d];  logits [videos]
+ *   cw1 [hc, d], cb1 [hc], cw2 [hc], cb2 [1] */
+EWVIT_API int ewvit_video_head_fwd(const float *fused, const float *space, const float *freq, int64_t videos, int k,
+                                   int d, float *mean_fused, float *mean_space, float *mean_freq, const float *cw1,
+                                   const float *cb1, const float *cw2, const float *cb2, int hc, float *logits,
+                                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,10 @@ manifest = {k: {"shape": list(v.shape), "dtype": str(v.dtype)} for k, v in model
 with open(os.path.join(HERE, "state_dict_manifest.json"), "w") as f:
     json.dump(manifest, f, indent=0, sort_keys=True)
 print("manifest entries:", len(manifest))
+# checksums of the reference's own seeded (torch.manual_seed(42)) random initialisation, every tensor
+init_sums = {k: float(v.double().sum()) for k, v in model.state_dict().items()}
+with open(os.path.join(HERE, "seeded_init_sums.json"), "w") as f:
+    json.dump(init_sums, f, indent=0, sort_keys=True)
 
 # ---- BatchNorm calibration scalars (part of the weight definition, see tests/_weights.py) ----
 CALIB_PATH = os.path.join(HERE, "bn_calibration.json")

@@ -1,0 +1,120 @@
+"""Host-side logic of the drop-in modules, no GPU: state_dict contract, seeded-init equivalence with the
+reference, chunk/position rule, error behaviour, weight re-layout helpers."""
+import json
+import os
+
+import pytest
+import torch
+
+from _weights import GOLDEN_DIR
+
+
+@pytest.fixture(scope="module")
+def model():
+    from network.model import DeepfakeDetector
+    torch.manual_seed(42)
+    return DeepfakeDetector(in_channels=3, dama_dim=128, batch_size=8)
+
+
+def test_state_dict_keys_shapes_dtypes_match_reference(model, manifest):
+    """Row a-1: every one of the reference's 1743 entries, same shape and dtype (strict load both ways)."""
+    sd = model.state_dict()
+    assert set(sd) == set(manifest)
+    for k, meta in manifest.items():
+        assert list(sd[k].shape) == meta["shape"], k
+        assert str(sd[k].dtype) == meta["dtype"], k
+    for k in ("dama.mwt.dwt.h0_col", "dama.mwt.hf_conv.seperate.2.1.running_var", "dama.sfe.pos_embedding",
+              "dama.cross_att.layers.1.3.to_kv.weight", "sfe_cls.efficient_net._blocks.15._se_expand.bias", "classifier.3.bias"):
+        assert k in sd
+
+
+def test_seeded_init_is_bit_identical_to_reference(model):
+    """Same construction order and initialisers: torch.manual_seed(42) gives the reference's weights."""
+    ref = json.load(open(os.path.join(GOLDEN_DIR, "seeded_init_sums.json")))
+    sd = model.state_dict()
+    bad = [k for k, s in ref.items() if abs(float(sd[k].double().sum()) - s) > 1e-9 * max(1.0, abs(s))]
+    assert not bad, bad[:5]
+
+
+def test_frozen_backbone_prefix(model):
+    """sfe.py:115-119: the first six backbone parameters do not train."""
+    flags = [p.requires_grad for _, p in model.dama.sfe.efficient_net.named_parameters()]
+    assert flags[:6] == [False] * 6 and all(flags[6:])
+
+
+def test_attribute_surface_used_by_reference_tools(model):
+    """utils/visualize_feature_maps.py:138-168 touches these."""
+    d = model.dama
+    assert hasattr(d.sfe.efficient_net, "features") and hasattr(d.mwt, "dwt") and callable(d.mwt.wavelet_transform)
+    assert callable(d._process_frame) and len(d.cross_att.layers) == 2 and len(d.cross_att.layers[0]) == 4
+    assert d.fusion_gate[0].kernel_size == (3, 3)
+    assert model.ablation_config == ["dynamic", "sfe_only", "sfe_mwt"]
+    assert not hasattr(model, "ablation")          # exists only after a forward / configure_ablation (model.py:77-78)
+    model.configure_ablation("sfe_mwt")
+    assert model.ablation == "sfe_mwt"
+    with pytest.raises(ValueError):
+        model.configure_ablation("nope")
+    del model.ablation
+
+
+def test_eval_forward_on_cpu_fails_loudly(model):
+    from ewvit import EwvitError
+    model.eval()
+    with pytest.raises(EwvitError, match="no CPU fallback"):
+        model(torch.zeros(1, 1, 3, 224, 224), 1, "dynamic")
+    with pytest.raises(EwvitError):
+        model.dama.mwt(torch.zeros(1, 3, 224, 224))
+    model.train()
+
+
+def test_chunk_position_rule():
+    """Frame (b, k) of a chunk [s, e) sits at row b*(e-s) + (k-s) of the flattened chunk (dama.py:183-186)."""
+    from ewvit.engine import check_chunk_limit, chunk_pos_index
+    idx = chunk_pos_index(2, 5, 2).view(2, 5)
+    assert idx.tolist() == [[0, 1, 0, 1, 0], [2, 3, 2, 3, 1]]
+    idx = chunk_pos_index(8, 64, 8).view(8, 64)
+    assert idx[3, 17].item() == 3 * 8 + 1 and int(idx.max()) == 63
+    check_chunk_limit(8, 300, 8, 64)
+    with pytest.raises(RuntimeError, match=r"tensor a \(65\).*tensor b \(64\)"):
+        check_chunk_limit(13, 5, 5, 64)
+    check_chunk_limit(13, 4, 5, 64)      # chunks are min(batch_size, K) long
+
+
+def test_fold_bn_and_tap_major_layout():
+    from ewvit import engine
+    torch.manual_seed(0)
+    conv, bn = torch.nn.Conv2d(5, 4, 3, padding=1), torch.nn.BatchNorm2d(4)
+    bn.running_mean.normal_()
+    bn.running_var.uniform_(0.5, 2)
+    bn.weight.data.normal_()
+    bn.bias.data.normal_()
+    bn.eval()
+    sd = {"c.weight": conv.weight.data, "c.bias": conv.bias.data, **{"b." + k: v for k, v in bn.state_dict().items()}}
+    scale, shift = engine._fold_bn(sd, "c.", "b.")
+    x = torch.randn(2, 5, 6, 6)
+    raw = torch.nn.functional.conv2d(x, conv.weight, None, padding=1)
+    assert torch.allclose(raw * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1), bn(conv(x)), atol=1e-5)
+    w = engine._conv_w_tapmajor(conv.weight.data, 64)
+    assert w.shape == (4, 3, 3, 64) and w.dtype == torch.bfloat16
+    assert torch.equal(w[2, 1, 0, :5].float(), conv.weight.data[2, :, 1, 0].bfloat16().float())
+    assert float(w[..., 5:].abs().max()) == 0.0
+
+
+def test_train_mode_torch_composition_matches_oracle_in_eval_math(model, manifest, monkeypatch):
+    """The PyTorch composition kept for training is the same math as the oracle: check the DAMA fusion tail and
+    the ViT head on CPU (sub-modules with no Haar kernel on their path), in eval mode via EWVIT_FORCE_TORCH."""
+    from _weights import fill_module_, seeded_randn
+    from oracle import ewvit_oracle as O
+    monkeypatch.setenv("EWVIT_FORCE_TORCH", "1")
+    fill_module_(model, seed=0)
+    model.eval()
+    sd = {k: v for k, v in model.state_dict().items()}
+    s, f = seeded_randn((3, 1, 128), 1), seeded_randn((3, 1, 128), 2)
+    with torch.no_grad():
+        a, b = model.dama.cross_att(s, f)
+        ra, rb = O.bidirectional_cross(sd, "dama.cross_att.", s, f, 4, 2)
+        assert torch.allclose(a, ra, atol=1e-5) and torch.allclose(b, rb, atol=1e-5)
+        feat = seeded_randn((2, 1280, 7, 7), 3) * 0.3
+        x = O.vit_tokens_from_features(sd, "dama.sfe.", feat)
+        assert torch.allclose(model.dama.sfe.transformer(x), O.vit_transformer(sd, "dama.sfe.", x), atol=1e-4)
+    model.train()
