@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the EWViT per-frame forward hot path (BASELINE.json metric: frames/sec of the EWViT forward at
+224x224, plus the fused MWT DWT kernel's HBM GB/s against peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+N = 1 : one process.  N > 1 : launched by the driver as
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+one rank per GPU; every rank scores its own shard of videos (weak scaling, no data-path collective) and the
+logits are gathered with one NCCL all_gather per step.
+
+Workload (configs[2] of BASELINE.json): full EWViT inference, dynamic mode, bf16 tensor-core math, 512 synthetic
+224x224 RGB frames per GPU per step = 8 videos x 64 frames, batch_size 8 (reference chunks of 64 frames),
+random-init weights (torch.manual_seed(42), the reference's own initialisers).  A step = one forward over the 512
+frames.  `value` times the steps with the frames already resident in HBM; `e2e` times the same steps through the
+public module call with pinned HOST frames (H2D copy + forward + D2H logits inside the timed region).
+
+--impl reference : the reference's CPU implementation of the path.  The reference is pure Python and cannot travel
+to the GPU box, so this arm times the oracle port (oracle/ewvit_oracle.py, validated against the unmodified
+reference by tests/golden) on the host cores, each step a bounded sample (one video x 8 frames) of the workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "efficient-wavelet-vit_b200"))
+sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+VIDEOS, FRAMES, BATCH_SIZE, SIDE = 8, 64, 8, 224
+METRIC = "frames/sec EWViT forward 224x224 (dynamic mode, bf16, batch 512 frames per GPU)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (debug)")
+    return ap.parse_args()
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[2]: full EWViT inference, ablation=dynamic, 8 videos x 64 frames x 3x224x224 per GPU, "
+                        "batch_size=8 (reference chunks of 64 frames), random-init weights seed 42",
+            "frames_per_gpu_per_step": VIDEOS * FRAMES, "global_frames_per_step": VIDEOS * FRAMES * n_gpus,
+            "parallelism": f"dp{n_gpus} (videos sharded by rank, NCCL all_gather of logits)" if n_gpus > 1 else "single GPU",
+            "l2_policy": "inputs+activations per step (~9 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md, 'clocks DURING the timed region')."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU legs
+def oracle_state_dict(model):
+    return {k: v.detach().float().cpu() for k, v in model.state_dict().items()
+            if k.startswith("dama.") or k.startswith("classifier.")}
+
+
+def time_cpu_oracle(sd, steps, warmup, budget_s=30.0):
+    """Oracle port on the host cores: x[1, 8, 3, 224, 224], batch_size 8 (BASELINE.json configs[0])."""
+    from oracle import ewvit_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x = torch.randn(1, 8, 3, SIDE, SIDE, generator=torch.Generator().manual_seed(42))
+    for _ in range(max(1, warmup)):
+        O.detector_forward(sd, x, 8, "dynamic")
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.detector_forward(sd, x, 8, "dynamic")
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    mean = sum(times) / len(times)
+    return {"value": 8.0 / mean, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} timed forwards of 1 video x 8 frames (batch_size 8, fp32, eval) through oracle/ewvit_oracle.py",
+            "ms_per_sample": mean * 1e3}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from network.model import DeepfakeDetector
+    torch.manual_seed(42)
+    model = DeepfakeDetector(3, 128, batch_size=BATCH_SIZE)
+    base = time_cpu_oracle(oracle_state_dict(model), args.steps, args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_sample"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- native arm
+def load_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device: libewvit.so has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from ewvit import engine
+    from ewvit._lib import load
+    from network.model import DeepfakeDetector
+    lib = load()
+
+    torch.manual_seed(42)
+    model = DeepfakeDetector(3, 128, batch_size=BATCH_SIZE)
+    sd_cpu = oracle_state_dict(model) if rank == 0 else None
+    model = model.to(dev).eval()
+
+    gen = torch.Generator().manual_seed(1000 + rank)
+    x_host = torch.randn(VIDEOS, FRAMES, 3, SIDE, SIDE, generator=gen).pin_memory()
+    x_dev = x_host.to(dev, non_blocking=True)
+    gathered = [torch.empty(VIDEOS, 1, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step_resident():
+        out = model(x_dev, BATCH_SIZE, "dynamic")
+        if world > 1:
+            dist.all_gather(gathered, out["logits"])
+        return out["logits"]
+
+    x_stage = torch.empty_like(x_dev)
+    logits_host = torch.empty(VIDEOS, 1).pin_memory()
+
+    def step_e2e():
+        x_stage.copy_(x_host, non_blocking=True)                 # H2D of this step's frames (pinned)
+        out = model(x_stage, BATCH_SIZE, "dynamic")
+        if world > 1:
+            dist.all_gather(gathered, out["logits"])
+        logits_host.copy_(out["logits"], non_blocking=True)      # D2H of the step's result
+        return logits_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with torch.no_grad():
+        for _ in range(max(3, args.warmup)):
+            step_resident()
+        logits = step_resident().float().cpu()
+        if not torch.isfinite(logits).all():
+            raise SystemExit("non-finite logits with the random-init weights: the run is invalid")
+
+        # ---- timed region 1: frames resident in HBM, per-stage CUDA events on the launching stream
+        engine.TIMER = engine.StageTimer()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = lib.ewvit_launch_count()
+        total_ms = timed(step_resident, args.steps)
+        launches = int(lib.ewvit_launch_count() - launches0)
+        clocks = sampler.stop()
+        stages = engine.TIMER.summary_ms()
+        engine.TIMER = None
+
+        # ---- timed region 2: end to end through the module call with pinned host frames
+        for _ in range(2):
+            step_e2e()
+        e2e_ms = timed(step_e2e, args.steps)
+
+        # ---- standalone fused DWT, BASELINE configs[1]: 256x3x224x224 fp32, all six outputs materialised
+        dwt = None
+        if rank == 0:
+            from ewvit import ops
+            xd = x_dev.view(-1, 3, SIDE, SIDE)[:256]
+            outs = ops.dwt3_haar(xd)
+            dwt_bytes = xd.numel() * 4 + sum(v.numel() * 4 for v in outs.values())
+            for _ in range(3):
+                ops.dwt3_haar(xd, out=outs)
+            torch.cuda.synchronize()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(21)]
+            evs[0].record()
+            for i in range(20):
+                ops.dwt3_haar(xd, out=outs)
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            dwt_ms = statistics.median(evs[i].elapsed_time(evs[i + 1]) for i in range(20))
+            dwt = (dwt_bytes, dwt_ms)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = load_peaks()
+    n_frames = VIDEOS * FRAMES
+    ms_per_step = total_ms / args.steps
+    value = world * n_frames * args.steps / (total_ms / 1e3)
+    e2e_value = world * n_frames * args.steps / (e2e_ms / 1e3)
+
+    # dominant kernel: multiscale_fusion 384->128 3x3 conv (implicit GEMM on tcgen05), one launch per step
+    ms_conv = stages["mwt.multiscale"][0]
+    conv_flops = 2.0 * n_frames * 112 * 112 * 128 * 9 * 384          # algorithmic FLOPs per launch (11.098 GFLOP/frame)
+    achieved = conv_flops / (ms_conv / 1e3) / 1e12
+    roofline = {"kernel": "gemm_tc_kernel<EPI_CONV> multiscale_fusion 384->128 @112x112 (mwt.py:68-72)", "bound": "tensor",
+                "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                "ms_per_launch": ms_conv, "flops_per_launch": conv_flops,
+                "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)"}
+    dwt_bytes_pipe = n_frames * 3 * SIDE * SIDE * 4 * 2              # frames read once + HF1-3 written once (LL never leaves the SM)
+    dwt_pipe_ms = stages["mwt.dwt3"][0]
+    extra = {
+        "stage_ms": {k: round(v[0] * v[1] / args.steps, 4) for k, v in sorted(stages.items())},
+        "dwt3_in_pipeline": {"bound": "hbm", "achieved": dwt_bytes_pipe / dwt_pipe_ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": dwt_bytes_pipe / dwt_pipe_ms / 1e6 / peaks["hbm_gbs"], "bytes_per_launch": dwt_bytes_pipe},
+        "dwt3_standalone_config2": {"bound": "hbm", "achieved": dwt[0] / dwt[1] / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": dwt[0] / dwt[1] / 1e6 / peaks["hbm_gbs"], "bytes_per_launch": dwt[0],
+                                    "ms_per_launch": dwt[1], "workload": "256x3x224x224 fp32, LL1-3 + HF1-3 written"},
+    }
+    cpu = None if args.no_cpu_baseline else time_cpu_oracle(sd_cpu, 8, 1, budget_s=25.0)
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": VIDEOS * 4,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, **extra,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -23,6 +23,53 @@ LN_EPS = 1e-5
 MACRO_BATCH = 512          # frames per pass: bounds the MWT workspace (~17 MB / frame)
 
 
+class StageTimer:
+    """Optional CUDA-event bracketing of the pipeline stages (bench.py turns it on; off by default).
+    Events are recorded on the current stream, so a bracket measures exactly the kernels launched inside it."""
+
+    def __init__(self):
+        self.records = {}
+
+    class _Span:
+        def __init__(self, timer, name):
+            self.timer, self.name = timer, name
+
+        def __enter__(self):
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+        def __exit__(self, *exc):
+            self.e1.record()
+            self.timer.records.setdefault(self.name, []).append((self.e0, self.e1))
+
+    def span(self, name):
+        return StageTimer._Span(self, name)
+
+    def summary_ms(self):
+        """name -> (mean ms per bracket, brackets).  Call after a device synchronize."""
+        return {k: (sum(a.elapsed_time(b) for a, b in v) / len(v), len(v)) for k, v in self.records.items()}
+
+    def reset(self):
+        self.records = {}
+
+
+class _NullSpan:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullSpan()
+TIMER = None               # set to a StageTimer to collect per-stage device times
+
+
+def stage(name):
+    return TIMER.span(name) if TIMER is not None else _NULL
+
+
 def _fold_bn(sd, conv, bn, eps=BN_EPS):
     """conv bias + eval BatchNorm -> per-channel (scale, shift) applied to the bias-free conv output."""
     scale = sd[bn + "weight"].float() / torch.sqrt(sd[bn + "running_var"].float() + eps)
@@ -102,18 +149,25 @@ class MwtRunner:
         ws = self._workspace(n, h, w)
         h1, w1, d = h // 2, w // 2, self.dim
         hf = ws["hf"]
-        ops.dwt3_haar(frames, out={"hf1": hf[0], "hf2": hf[1], "hf3": hf[2]}, want=("hf1", "hf2", "hf3"))
+        with stage("mwt.dwt3"):
+            ops.dwt3_haar(frames, out={"hf1": hf[0], "hf2": hf[1], "hf3": hf[2]}, want=("hf1", "hf2", "hf3"))
         for lvl in range(3):
-            ops.mwt_head(hf[lvl].view(n, 9, h >> (lvl + 1), w >> (lvl + 1)), self.head_w, self.head_scale,
-                         self.head_shift, ws["head"], h1, w1)
-            ops.conv3x3_bf16(ws["head"], self.fus_w, n, h1, w1, 1, True, self.fus_scale, self.fus_shift, True,
-                             ws["cat"], lvl * d, True)
-        ops.conv3x3_bf16(ws["cat"], self.ms_w, n, h1, w1, 1, True, self.ms_scale, self.ms_shift, True, ws["ms"], 0, True)
-        ops.conv3x3_bf16(ws["ms"], self.fc_w, n, h1, w1, 2, True, self.fc_scale, self.fc_shift, True, ws["fc"], 0, False)
-        ops.maxpool2x2(ws["fc"], ws["mp"])
-        hp, wp = ws["mp"].shape[1:3]
-        ops.conv3x3_bf16(ws["mp"], self.fp_w, n, hp, wp, 2, False, self.fp_scale, self.fp_shift, True, ws["pc"], 0, False)
-        return ops.gap(ws["pc"], out)
+            with stage("mwt.head"):
+                ops.mwt_head(hf[lvl].view(n, 9, h >> (lvl + 1), w >> (lvl + 1)), self.head_w, self.head_scale,
+                             self.head_shift, ws["head"], h1, w1)
+            with stage("mwt.hf_fusion"):
+                ops.conv3x3_bf16(ws["head"], self.fus_w, n, h1, w1, 1, True, self.fus_scale, self.fus_shift, True,
+                                 ws["cat"], lvl * d, True)
+        with stage("mwt.multiscale"):
+            ops.conv3x3_bf16(ws["cat"], self.ms_w, n, h1, w1, 1, True, self.ms_scale, self.ms_shift, True, ws["ms"], 0, True)
+        with stage("mwt.freq_conv"):
+            ops.conv3x3_bf16(ws["ms"], self.fc_w, n, h1, w1, 2, True, self.fc_scale, self.fc_shift, True, ws["fc"], 0, False)
+        with stage("mwt.pool_tail"):
+            ops.maxpool2x2(ws["fc"], ws["mp"])
+            hp, wp = ws["mp"].shape[1:3]
+            ops.conv3x3_bf16(ws["mp"], self.fp_w, n, hp, wp, 2, False, self.fp_scale, self.fp_shift, True, ws["pc"], 0, False)
+            res = ops.gap(ws["pc"], out)
+        return res
 
 
 # ------------------------------------------------------------------------------------------ SFE
@@ -209,7 +263,12 @@ class SfeRunner:
         """feat_nhwc: bf16 [n, ph*pw*channels] (NHWC flatten of the backbone map); pos_index int32 [n]."""
         n = feat_nhwc.shape[0]
         ws = self._workspace(n, feat_nhwc.device)
-        ops.linear_bf16(feat_nhwc, self.patch_w, shift=self.patch_b, out=ws["emb"], splits=ws["splits"], workspace=ws["ws"])
+        with stage("sfe.patch_embed"):
+            ops.linear_bf16(feat_nhwc, self.patch_w, shift=self.patch_b, out=ws["emb"], splits=ws["splits"], workspace=ws["ws"])
+        with stage("sfe.vit"):
+            return self._vit(ws, n, pos_index, out)
+
+    def _vit(self, ws, n, pos_index, out):
         x, y = ws["x"]
         ops.vit_assemble(ws["emb"], self.cls, self.pos, pos_index, out=x)
         for L in self.layers:
@@ -239,9 +298,10 @@ class SfeRunner:
         return f.permute(0, 2, 3, 1).reshape(n, -1)              # view when channels-last
 
     def forward(self, frames, pos_index, out=None):
-        feat = self.features(frames)
-        if not feat.is_contiguous():
-            feat = feat.contiguous()
+        with stage("sfe.backbone"):
+            feat = self.features(frames)
+            if not feat.is_contiguous():
+                feat = feat.contiguous()
         return self.head(feat, pos_index, out)
 
 
@@ -309,7 +369,8 @@ class DamaRunner:
         """frames [n,3,H,W] -> (fused, space, freq) each [n, dim] fp32 (``_process_frame``, dama.py:130-169)."""
         space = self.sfe.forward(frames, pos_index)
         freq = self.mwt.forward(frames)
-        return ops.dama_tail(space, freq, self.wpack, self.heads, self.depth, LN_EPS)
+        with stage("dama.tail"):
+            return ops.dama_tail(space, freq, self.wpack, self.heads, self.depth, LN_EPS)
 
     def forward_frames(self, x, batch_size):
         """x [B,K,3,H,W] fp32 CUDA -> per-frame (fused, space, freq) [B*K, dim] in (b, k) order."""
