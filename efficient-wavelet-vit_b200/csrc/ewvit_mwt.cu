@@ -20,7 +20,8 @@ constexpr int kWPitch = 28;             // 27 weights per output channel, padded
 constexpr int kOutC = 64;               // 54 real + 10 zero channels
 constexpr int kUpBytes = 9 * kHalo * kHaloPitch * 4;                    // 12960
 constexpr int kWBytes = (3 * kOcPerGroup * kWPitch + 2 * 56) * 4;       // 6496
-constexpr int kHeadSmem = kUpBytes + kWBytes + kTile * kTile * kOutC * 2;   // 52224
+constexpr int kOutPitchW = 33;          // 32 words (64 bf16) per pixel + 1 pad word: conflict-free column access
+constexpr int kHeadSmem = kUpBytes + kWBytes + kTile * kTile * kOutPitchW * 4;   // 53248
 
 struct HeadParams {
     const float *hf;      // [n, 9, hin, win]  (colour-major, subband-minor: the reference's reshape at mwt.py:77)
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(kHeadThreads) mwt_head_kernel(const HeadParams
     float *s_w = reinterpret_cast<float *>(head_smem + kUpBytes);
     float *s_scale = s_w + 3 * kOcPerGroup * kWPitch;
     float *s_shift = s_scale + 56;
-    __nv_bfloat16 (*s_out)[kOutC] = reinterpret_cast<__nv_bfloat16 (*)[kOutC]>(head_smem + kUpBytes + kWBytes);
+    uint32_t *s_out = reinterpret_cast<uint32_t *>(head_smem + kUpBytes + kWBytes);   // [256 px][33 words]
 
     const int tid = threadIdx.x;
     const int tiles_x = (p.wout + kTile - 1) / kTile;
@@ -90,67 +91,75 @@ __global__ void __launch_bounds__(kHeadThreads) mwt_head_kernel(const HeadParams
     }
     __syncthreads();
 
-    // ---- 3 -> 18 conv for one colour group on a quad of 4 horizontally adjacent pixels
+    // ---- 3 -> 18 conv for one colour group on 4 vertically adjacent pixels.  Consecutive lanes own
+    //      consecutive columns, so with the 33-word pixel pitch of s_out the packed bf16x2 stores below hit
+    //      distinct banks (a 32-word pitch made every lane of a warp collide on one bank).
     {
-        const int g = tid / 64, quad = tid % 64;
-        const int qy = quad / 4, qx = (quad % 4) * 4;
-        float in[3][3][6];
+        const int g = tid / 64, sub = tid % 64;
+        const int col = sub % kTile, r0 = (sub / kTile) * 4;
+        float in[3][6][3];
 #pragma unroll
         for (int ic = 0; ic < 3; ++ic)
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
+            for (int dy = 0; dy < 6; ++dy)
 #pragma unroll
-                for (int dx = 0; dx < 6; ++dx) in[ic][dy][dx] = s_up[g * 3 + ic][qy + dy][qx + dx];
-#pragma unroll 2
-        for (int oc = 0; oc < kOcPerGroup; ++oc) {
-            const float4 *wp = reinterpret_cast<const float4 *>(&s_w[(g * kOcPerGroup + oc) * kWPitch]);
-            float wv[28];
+                for (int dx = 0; dx < 3; ++dx) in[ic][dy][dx] = s_up[g * 3 + ic][r0 + dy][col + dx];
+#pragma unroll 1
+        for (int oc = 0; oc < kOcPerGroup; oc += 2) {
+            float a[2][4];
 #pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const float4 t = wp[i];
-                wv[4 * i] = t.x; wv[4 * i + 1] = t.y; wv[4 * i + 2] = t.z; wv[4 * i + 3] = t.w;
+            for (int o = 0; o < 2; ++o) {
+                const float4 *wp = reinterpret_cast<const float4 *>(&s_w[(g * kOcPerGroup + oc + o) * kWPitch]);
+                float wv[28];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    const float4 t = wp[i];
+                    wv[4 * i] = t.x; wv[4 * i + 1] = t.y; wv[4 * i + 2] = t.z; wv[4 * i + 3] = t.w;
+                }
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int ic = 0; ic < 3; ++ic)
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const float wk = wv[ic * 9 + dy * 3 + dx];
+                            a0 = fmaf(wk, in[ic][dy][dx], a0);
+                            a1 = fmaf(wk, in[ic][dy + 1][dx], a1);
+                            a2 = fmaf(wk, in[ic][dy + 2][dx], a2);
+                            a3 = fmaf(wk, in[ic][dy + 3][dx], a3);
+                        }
+                const int ch = g * kOcPerGroup + oc + o;
+                const float sc = s_scale[ch], sh = s_shift[ch];
+                a[o][0] = fmaxf(fmaf(a0, sc, sh), 0.f);
+                a[o][1] = fmaxf(fmaf(a1, sc, sh), 0.f);
+                a[o][2] = fmaxf(fmaf(a2, sc, sh), 0.f);
+                a[o][3] = fmaxf(fmaf(a3, sc, sh), 0.f);
             }
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            const int word = (g * kOcPerGroup + oc) >> 1;      // channels (oc, oc+1) share one 32-bit word
 #pragma unroll
-            for (int ic = 0; ic < 3; ++ic)
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const float wk = wv[ic * 9 + dy * 3 + dx];
-                        a0 = fmaf(wk, in[ic][dy][dx], a0);
-                        a1 = fmaf(wk, in[ic][dy][dx + 1], a1);
-                        a2 = fmaf(wk, in[ic][dy][dx + 2], a2);
-                        a3 = fmaf(wk, in[ic][dy][dx + 3], a3);
-                    }
-            const int ch = g * kOcPerGroup + oc;
-            const float sc = s_scale[ch], sh = s_shift[ch];
-            const int px = qy * kTile + qx;
-            s_out[px + 0][ch] = __float2bfloat16_rn(fmaxf(fmaf(a0, sc, sh), 0.f));
-            s_out[px + 1][ch] = __float2bfloat16_rn(fmaxf(fmaf(a1, sc, sh), 0.f));
-            s_out[px + 2][ch] = __float2bfloat16_rn(fmaxf(fmaf(a2, sc, sh), 0.f));
-            s_out[px + 3][ch] = __float2bfloat16_rn(fmaxf(fmaf(a3, sc, sh), 0.f));
+            for (int k = 0; k < 4; ++k) {
+                const __nv_bfloat162 v = __floats2bfloat162_rn(a[0][k], a[1][k]);
+                s_out[((r0 + k) * kTile + col) * kOutPitchW + word] = *reinterpret_cast<const uint32_t *>(&v);
+            }
         }
         if (g == 2) {
-            const int px = qy * kTile + qx;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
 #pragma unroll
-                for (int ch = 54; ch < kOutC; ++ch) s_out[px + k][ch] = __float2bfloat16_rn(0.f);
+                for (int word = 27; word < 32; ++word) s_out[((r0 + k) * kTile + col) * kOutPitchW + word] = 0u;
         }
     }
     __syncthreads();
 
-    // ---- coalesced 16-byte stores: one output pixel = 128 contiguous bytes of the NHWC tensor
+    // ---- one warp stores one pixel (32 words = 128 contiguous bytes of the NHWC tensor) per instruction
     const int wp_ = p.wout + 2;
-    __nv_bfloat16 *ybase = p.y + (long long)img * (p.hout + 2) * wp_ * kOutC;
-    for (int i = tid; i < kTile * kTile * 8; i += kHeadThreads) {
-        const int px = i / 8, part = i % 8;
+    uint32_t *ybase = reinterpret_cast<uint32_t *>(p.y + (long long)img * (p.hout + 2) * wp_ * kOutC);
+    const int lane = tid & 31;
+    for (int px = tid >> 5; px < kTile * kTile; px += kHeadThreads / 32) {
         const int oy = y0 + px / kTile, ox = x0 + px % kTile;
-        if (oy < p.hout && ox < p.wout) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(&s_out[px][part * 8]);
-            *reinterpret_cast<uint4 *>(ybase + ((long long)(oy + 1) * wp_ + (ox + 1)) * kOutC + part * 8) = v;
-        }
+        if (oy < p.hout && ox < p.wout)
+            ybase[((long long)(oy + 1) * wp_ + (ox + 1)) * (kOutC / 2) + lane] = s_out[px * kOutPitchW + lane];
     }
 }
 
