@@ -29,7 +29,7 @@ constexpr int kTileBytes = BM * BK * 2;        // 16 KiB
 constexpr int kStageBytes = 2 * kTileBytes;    // A + B
 constexpr int kEpiWarps = 8;                   // 2 warps per TMEM lane quarter, each takes half the columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;  // 320
-enum { EPI_CONV = 0, EPI_LINEAR = 1, EPI_PARTIAL = 2 };
+enum { EPI_CONV = 0, EPI_LINEAR = 1, EPI_PARTIAL = 2, EPI_BB = 3 };
 constexpr uint32_t kTmemCols = kAccStages * BN;   // 256
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 
@@ -60,6 +60,7 @@ struct GemmParams {
     long long ldr;
     int pad_hp, pad_wp;
     float *partial;
+    const __nv_bfloat16 *residual_bf16;   // EPI_BB: optional bf16 residual, same layout as the output
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -146,7 +147,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         if (lane == 0) {
             // ------------------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc = ewvit::umma_idesc_bf16(BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -155,6 +155,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int sp = (int)((w / p.tiles_n) / p.tiles_m);
                 const int kb0 = sp * p.kb_per_split;
                 const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                // columns past N are zero-filled B rows: shrink the MMA's N to the valid part (multiple of 16)
+                const int n_valid = min(BN, p.N - (int)(w % p.tiles_n) * BN);
+                const uint32_t idesc = ewvit::umma_idesc_bf16(BM, (uint32_t)((n_valid + 15) & ~15));
                 ewvit::mbar_wait(ewvit::smem_u32(&tempty[acc]), acc_phase ^ 1);
                 ewvit::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -190,11 +193,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m_t = (int)(wm % p.tiles_m);
             const int sp = (int)(wm / p.tiles_m);
 
-            if (kEpi == EPI_CONV && n_t != cur_nt) {   // (re)stage the per-channel scale/shift of this column tile
+            if ((kEpi == EPI_CONV || kEpi == EPI_BB) && n_t != cur_nt) {   // (re)stage the per-channel scale/shift of this column tile
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                 if (etid < BN) {
-                    s_scale[etid] = p.scale ? p.scale[n_t * BN + etid] : 1.f;
-                    s_shift[etid] = p.shift ? p.shift[n_t * BN + etid] : 0.f;
+                    const bool in = n_t * BN + etid < p.N;
+                    s_scale[etid] = (p.scale && in) ? p.scale[n_t * BN + etid] : 1.f;
+                    s_shift[etid] = (p.shift && in) ? p.shift[n_t * BN + etid] : 0.f;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                 cur_nt = n_t;
@@ -226,11 +230,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
                 const int c = hc * 2 + cc;
+                if (kEpi == EPI_BB && n_t * BN + c * 32 >= p.N) continue;   // warp-uniform: nothing valid in this chunk
                 uint32_t v[32];
                 ewvit::tmem_ld_32x32(t_row + c * 32, v);
                 ewvit::tmem_ld_wait();
                 const int col0 = n_t * BN + c * 32;
                 if (!valid) continue;
+                if (kEpi == EPI_BB) {
+                    // bias (+ SiLU / ReLU) (+ bf16 residual) -> bf16, 8 columns (16 bytes) at a time, masked past N
+                    __nv_bfloat16 *orow_p = static_cast<__nv_bfloat16 *>(p.out) + orow * p.ldo + p.col_off;
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        const int col = col0 + g8 * 8;
+                        if (col >= p.N) break;
+                        float f8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f8[i] = __uint_as_float(v[g8 * 8 + i]) + s_shift[c * 32 + g8 * 8 + i];
+                        if (p.act == 3) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f8[i] = __fdividef(f8[i], 1.f + __expf(-f8[i]));
+                        } else if (p.act == 1) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f8[i] = fmaxf(f8[i], 0.f);
+                        }
+                        if (p.residual_bf16) {   // skip connection is added AFTER the activation (FusedMBConv/MBConv)
+                            const uint4 rv = *reinterpret_cast<const uint4 *>(p.residual_bf16 + orow * p.ldr + col);
+                            const __nv_bfloat162 *rp = reinterpret_cast<const __nv_bfloat162 *>(&rv);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 r2 = __bfloat1622float2(rp[i]);
+                                f8[2 * i] += r2.x;
+                                f8[2 * i + 1] += r2.y;
+                            }
+                        }
+                        uint4 pk;
+                        __nv_bfloat162 b0 = __floats2bfloat162_rn(f8[0], f8[1]), b1 = __floats2bfloat162_rn(f8[2], f8[3]);
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(f8[4], f8[5]), b3 = __floats2bfloat162_rn(f8[6], f8[7]);
+                        pk.x = *reinterpret_cast<uint32_t *>(&b0);
+                        pk.y = *reinterpret_cast<uint32_t *>(&b1);
+                        pk.z = *reinterpret_cast<uint32_t *>(&b2);
+                        pk.w = *reinterpret_cast<uint32_t *>(&b3);
+                        *reinterpret_cast<uint4 *>(orow_p + col) = pk;
+                    }
+                    continue;
+                }
                 if (kEpi == EPI_PARTIAL) {
                     float4 *dst = reinterpret_cast<float4 *>(p.partial + ((long long)sp * p.M + orow) * p.N + col0);
 #pragma unroll
@@ -357,6 +400,7 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmPara
 
 int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int epi, cudaStream_t stream) {
     if (epi == EPI_CONV) return launch_gemm_t<EPI_CONV>(tmA, tmB, p, stream);
+    if (epi == EPI_BB) return launch_gemm_t<EPI_BB>(tmA, tmB, p, stream);
     if (epi == EPI_PARTIAL) return launch_gemm_t<EPI_PARTIAL>(tmA, tmB, p, stream);
     return launch_gemm_t<EPI_LINEAR>(tmA, tmB, p, stream);
 }
@@ -531,4 +575,86 @@ extern "C" int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, in
             }
     }
     return launch_gemm(tmA, tmB, p, EPI_CONV, (cudaStream_t)stream);
+}
+
+
+// General NHWC bf16 convolution for the EfficientNet backbone (1x1 or 3x3/pad 1, stride 1 or 2) with a fused
+// bias + optional bf16 residual + activation epilogue.  Channel counts only need to be multiples of 8: the K and N
+// tails are zero-filled by TMA (boxes may overhang the tensor) and masked in the epilogue.
+extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, int wd, int cin, int cout, int ksize,
+                                    int stride, const float *bias, int act, const void *residual, void *y, void *stream) {
+    EWVIT_REQUIRE(n >= 0 && h > 0 && wd > 0 && cin > 0 && cout > 0, EWVIT_ERR_INVALID_ARG, "ewvit_conv_nhwc_bf16: bad sizes");
+    if (n == 0) return EWVIT_OK;
+    EWVIT_REQUIRE(x && w && y, EWVIT_ERR_INVALID_ARG, "ewvit_conv_nhwc_bf16: NULL pointer");
+    EWVIT_REQUIRE((ksize == 1 && stride == 1) || (ksize == 3 && (stride == 1 || stride == 2)), EWVIT_ERR_UNSUPPORTED,
+                  "ewvit_conv_nhwc_bf16: supports 1x1/stride 1 and 3x3/stride 1|2 (got k=%d s=%d)", ksize, stride);
+    EWVIT_REQUIRE(cin % 8 == 0 && cout % 8 == 0, EWVIT_ERR_UNSUPPORTED,
+                  "ewvit_conv_nhwc_bf16: channel counts must be multiples of 8 (got cin=%d cout=%d)", cin, cout);
+    EWVIT_REQUIRE(act == 0 || act == 1 || act == 3, EWVIT_ERR_INVALID_ARG, "ewvit_conv_nhwc_bf16: act must be 0 (none), 1 (relu) or 3 (silu)");
+    EWVIT_REQUIRE(ewvit_aligned16(x) && ewvit_aligned16(w) && ewvit_aligned16(y) && ewvit_aligned16(residual), EWVIT_ERR_INVALID_ARG,
+                  "ewvit_conv_nhwc_bf16: pointers must be 16-byte aligned");
+    int rc = ewvit_check_device();
+    if (rc != EWVIT_OK) return rc;
+
+    const int ho = (h - 1) / stride + 1, wo = (wd - 1) / stride + 1;
+    GemmParams p = {};
+    p.N = cout;
+    p.tiles_n = (cout + BN - 1) / BN;
+    p.splits = 1;
+    p.out = y; p.out_fp32 = 0; p.ldo = cout; p.col_off = 0;
+    p.shift = bias; p.act = act;
+    p.residual_bf16 = static_cast<const __nv_bfloat16 *>(residual);
+    p.ldr = cout;
+    CUtensorMap tmA, tmB;
+    if (ksize == 1) {
+        const long long rows = (long long)n * h * wd;
+        const int num_kb = (cin + BK - 1) / BK;
+        uint64_t dims[2] = {(uint64_t)cin, (uint64_t)rows}, str[2] = {2, (uint64_t)cin * 2};
+        uint32_t box[2] = {BK, BM};
+        rc = ewvit_make_tmap_bf16(&tmA, x, 2, dims, str, box, nullptr);
+        if (rc != EWVIT_OK) return rc;
+        uint64_t dimsb[2] = {(uint64_t)cin, (uint64_t)cout};
+        uint32_t boxb[2] = {BK, BN};
+        rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, str, boxb, nullptr);
+        if (rc != EWVIT_OK) return rc;
+        p.a_mode = A_FLAT;
+        p.chunks_per_tap = num_kb;
+        p.num_kb = num_kb;
+        p.kb_per_split = num_kb;
+        p.M = rows;
+        p.tiles_m = (int)((rows + BM - 1) / BM);
+    } else {
+        const int chunks = (cin + BK - 1) / BK;
+        const int kpad = chunks * BK;
+        uint64_t dimsb[2] = {(uint64_t)9 * kpad, (uint64_t)cout}, strb[2] = {2, (uint64_t)9 * kpad * 2};
+        uint32_t boxb[2] = {BK, BN};
+        rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, strb, boxb, nullptr);
+        if (rc != EWVIT_OK) return rc;
+        const int box_w = 16, box_h = 8;
+        uint64_t dims[4] = {(uint64_t)cin, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
+        uint64_t str[4] = {2, (uint64_t)cin * 2, (uint64_t)wd * cin * 2, (uint64_t)h * wd * cin * 2};
+        uint32_t box[4] = {BK, (uint32_t)(box_w * stride), (uint32_t)(box_h * stride), 1};
+        uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+        rc = ewvit_make_tmap_bf16(&tmA, x, 4, dims, str, box, es);
+        if (rc != EWVIT_OK) return rc;
+        p.a_mode = A_TILE4D;
+        p.chunks_per_tap = chunks;
+        p.num_kb = 9 * chunks;
+        p.kb_per_split = p.num_kb;
+        p.box_w = box_w; p.box_h = box_h; p.in_stride = stride;
+        p.tiles_x = (wo + box_w - 1) / box_w;
+        p.tiles_y = (ho + box_h - 1) / box_h;
+        p.tiles_m = p.tiles_x * p.tiles_y * n;
+        p.out_w = wo; p.out_h = ho;
+        p.out_pad = 0;
+        p.out_wp = wo;
+        p.out_img_rows = (long long)ho * wo;
+        p.M = (long long)n * p.out_img_rows;
+        for (int dy = 0; dy < 3; ++dy)
+            for (int dx = 0; dx < 3; ++dx) {
+                p.tap_a0[dy * 3 + dx] = dx - 1;
+                p.tap_a1[dy * 3 + dx] = dy - 1;
+            }
+    }
+    return launch_gemm(tmA, tmB, p, EPI_BB, (cudaStream_t)stream);
 }

@@ -38,6 +38,10 @@ SIGNATURES = {
     "ewvit_vit_attention": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
     "ewvit_dama_wpack_floats": (c_int64, [c_int, c_int]),
     "ewvit_dama_tail_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, P, c_float, P, P, P, P]),
+    "ewvit_conv_nhwc_bf16": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, P]),
+    "ewvit_stem_conv_fwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P]),
+    "ewvit_dwconv3x3_nhwc_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "ewvit_se_apply_nhwc_bf16": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "ewvit_video_head_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P, P, P, P, P, c_int, P, P]),
 }
 

@@ -171,6 +171,15 @@ class MwtRunner:
 
 
 # ------------------------------------------------------------------------------------------ SFE
+def make_backbone(features: nn.Module, device, v2s: bool):
+    """V2-S (torchvision) -> native kernels; anything else (the b0 ablation branches), or EWVIT_BACKBONE=cudnn ->
+    the cuDNN bf16 channels-last copy."""
+    import os
+    if v2s and os.environ.get("EWVIT_BACKBONE", "native") != "cudnn":
+        return NativeEffNetV2(features, device)
+    return fused_bf16_backbone(features, device)
+
+
 def fused_bf16_backbone(features: nn.Module, device):
     """Inference copy of an EfficientNet feature extractor: BatchNorm folded into the preceding conv,
     bf16, channels-last (so the [N,1280,7,7] output is NHWC in memory and the reference's
@@ -186,6 +195,106 @@ def fused_bf16_backbone(features: nn.Module, device):
 
     fuse(net)
     return net.to(device=device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+
+
+def _fold_conv_bn(conv, bn):
+    """fp32 (weight, bias) of conv followed by eval-mode BatchNorm."""
+    w = conv.weight.detach().float()
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    bias = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    if conv.bias is not None:
+        bias = bias + conv.bias.detach().float() * scale
+    return w * scale.view(-1, 1, 1, 1), bias.contiguous()
+
+
+def _w3x3_tapmajor_padded(w):
+    """[cout, cin, 3, 3] fp32 -> bf16 [cout, 9, ceil(cin/64)*64] with zero padding (layout of ewvit_conv_nhwc_bf16)."""
+    cout, cin = w.shape[:2]
+    cpad = (cin + 63) // 64 * 64
+    out = torch.zeros((cout, 9, cpad), dtype=torch.bfloat16, device=w.device)
+    out[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin).to(torch.bfloat16)
+    return out.contiguous()
+
+
+class NativeEffNetV2:
+    """torchvision ``efficientnet_v2_s(...).features`` (sfe.py:111-113,150) in eval mode on the native kernels:
+    FusedMBConv 3x3 convs, 1x1 expand/project convs and the 1x1 head on the tcgen05 implicit-GEMM kernel with
+    bias + SiLU + residual fused into the epilogue; depthwise 3x3 + SiLU + SE squeeze in one kernel; SE gate +
+    scaling in one kernel; the stem reads the fp32 NCHW frames directly.  NHWC bf16 activations, BatchNorm folded."""
+
+    def __init__(self, features: nn.Module, device):
+        dev = torch.device(device)
+        self.device = dev
+        self.ops = []
+        mods = list(features)
+        stem = mods[0]
+        w, b = _fold_conv_bn(stem[0], stem[1])
+        if tuple(stem[0].kernel_size) != (3, 3) or tuple(stem[0].stride) != (2, 2) or w.shape[1] != 3:
+            raise EwvitError("native backbone: unexpected stem")
+        self.ops.append(("stem", w.to(dev).contiguous(), b.to(dev)))
+        for stage in mods[1:-1]:
+            for blk in stage:
+                kind = type(blk).__name__
+                layers = list(blk.block)
+                res = bool(blk.use_res_connect)
+                if kind == "FusedMBConv":
+                    c0 = layers[0]
+                    w, b = _fold_conv_bn(c0[0], c0[1])
+                    stride = c0[0].stride[0]
+                    if len(layers) == 1:
+                        self.ops.append(("conv3", _w3x3_tapmajor_padded(w).to(dev), b.to(dev), stride, "silu", res, True))
+                    else:
+                        self.ops.append(("conv3", _w3x3_tapmajor_padded(w).to(dev), b.to(dev), stride, "silu", False, False))
+                        w2, b2 = _fold_conv_bn(layers[1][0], layers[1][1])
+                        self.ops.append(("conv1", w2.flatten(1).to(torch.bfloat16).to(dev).contiguous(), b2.to(dev), None, res, True))
+                elif kind == "MBConv":
+                    ex, dw, se, pr = layers
+                    w, b = _fold_conv_bn(ex[0], ex[1])
+                    self.ops.append(("conv1", w.flatten(1).to(torch.bfloat16).to(dev).contiguous(), b.to(dev), "silu", False, False))
+                    wd_, bd = _fold_conv_bn(dw[0], dw[1])
+                    c = wd_.shape[0]
+                    self.ops.append(("dw", wd_.reshape(c, 9).t().contiguous().to(dev), bd.to(dev), dw[0].stride[0]))
+                    self.ops.append(("se", se.fc1.weight.detach().float().flatten(1).contiguous().to(dev),
+                                     se.fc1.bias.detach().float().to(dev),
+                                     se.fc2.weight.detach().float().flatten(1).t().contiguous().to(dev),
+                                     se.fc2.bias.detach().float().to(dev)))
+                    w2, b2 = _fold_conv_bn(pr[0], pr[1])
+                    self.ops.append(("conv1", w2.flatten(1).to(torch.bfloat16).to(dev).contiguous(), b2.to(dev), None, res, True))
+                else:
+                    raise EwvitError(f"native backbone: unsupported block {kind}")
+        head = mods[-1]
+        w, b = _fold_conv_bn(head[0], head[1])
+        self.ops.append(("conv1", w.flatten(1).to(torch.bfloat16).to(dev).contiguous(), b.to(dev), "silu", False, False))
+
+    def forward(self, frames):
+        """fp32 [n,3,H,W] -> bf16 NHWC [n, H/32, W/32, C_out]."""
+        block_in = None      # input of the current residual block
+        x = None
+        pooled = None
+        for i, op in enumerate(self.ops):
+            kind = op[0]
+            with stage(f"bb.{kind}" if TIMER is None or not getattr(TIMER, "per_layer", False) else f"bb.{i:03d}.{kind}"):
+                if kind == "stem":
+                    x = ops.stem_conv(frames, op[1], op[2])
+                    block_in = x
+                elif kind == "conv3":
+                    _, w, b, stride, act, res, ends = op
+                    x = ops.conv_nhwc_bf16(x, w, 3, stride, bias=b, act=act, residual=block_in if res else None)
+                    if ends:
+                        block_in = x
+                elif kind == "conv1":
+                    _, w, b, act, res, ends = op
+                    x = ops.conv_nhwc_bf16(x, w, 1, 1, bias=b, act=act, residual=block_in if res else None)
+                    if ends:
+                        block_in = x
+                elif kind == "dw":
+                    _, w, b, stride = op
+                    n, h, wd, c = x.shape
+                    pooled = torch.empty((n, c), dtype=torch.float32, device=x.device)
+                    x = ops.dwconv3x3(x, w, b, stride, pooled=pooled)
+                elif kind == "se":
+                    ops.se_apply(x, pooled, op[1], op[2], op[3], op[4])
+        return x
 
 
 class SfeRunner:
@@ -292,6 +401,9 @@ class SfeRunner:
 
     def features(self, frames):
         """fp32 frames [n,3,H,W] -> bf16 [n, 62720] NHWC-flattened backbone features."""
+        if isinstance(self.backbone, NativeEffNetV2):
+            f = self.backbone.forward(frames)                    # NHWC bf16
+            return f.reshape(f.shape[0], -1)
         x = frames.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
         f = self.backbone(x)                                     # [n, C, ph, pw], channels-last memory
         n = f.shape[0]

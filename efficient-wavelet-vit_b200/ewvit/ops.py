@@ -270,3 +270,73 @@ def video_head(fused, space, freq, videos, k, classifier=None):
                                           _ptr(ms), _ptr(mq), _ptr(cw1), _ptr(cb1), _ptr(cw2), _ptr(cb2), hc,
                                           _ptr(logits), _stream()), "ewvit_video_head_fwd")
     return mf, ms, mq, logits
+
+
+ACT_BB = {None: 0, "none": 0, "relu": 1, "silu": 3}
+
+
+def conv_nhwc_bf16(x, w, ksize, stride, bias=None, act=None, residual=None, out=None):
+    """Dense NHWC bf16 conv (1x1, or 3x3/pad 1) with fused bias/act/residual.  x [n,h,w,cin]; w [cout,cin] or
+    [cout,9,cin_pad]; returns [n,ho,wo,cout] bf16."""
+    _check_bf16(x, "x", 4)
+    _check_bf16(w, "w")
+    n, h, wd, cin = x.shape
+    cout = w.shape[0]
+    ho, wo = (h - 1) // stride + 1, (wd - 1) // stride + 1
+    if out is None:
+        out = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
+    elif out.numel() != n * ho * wo * cout or out.dtype != torch.bfloat16 or not out.is_contiguous():
+        raise EwvitError("conv_nhwc_bf16: bad out tensor")
+    if residual is not None:
+        _check_bf16(residual, "residual")
+        if residual.numel() != out.numel():
+            raise EwvitError("conv_nhwc_bf16: residual must match the output")
+    bias = _f32_or_none(bias, "bias", cout)
+    with torch.cuda.device(x.device):
+        check(load().ewvit_conv_nhwc_bf16(x.data_ptr(), w.data_ptr(), n, h, wd, cin, cout, ksize, stride, _ptr(bias),
+                                          ACT_BB[act], _ptr(residual), out.data_ptr(), _stream()), "ewvit_conv_nhwc_bf16")
+    return out
+
+
+def stem_conv(x, w, bias, out=None):
+    """fp32 NCHW frames [n,3,h,w] -> bf16 NHWC [n,h/2,w/2,cout]: conv3x3 s2 + bias + SiLU."""
+    _check_f32(x, "x")
+    _check_f32(w, "w")
+    n, c, h, wd = x.shape
+    cout = w.shape[0]
+    if c != 3 or w.numel() != cout * 27:
+        raise EwvitError("stem_conv: expects 3 input channels and [cout,3,3,3] weights")
+    bias = _f32_or_none(bias, "bias", cout)
+    if out is None:
+        out = torch.empty((n, (h - 1) // 2 + 1, (wd - 1) // 2 + 1, cout), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().ewvit_stem_conv_fwd(x.data_ptr(), n, h, wd, w.data_ptr(), bias.data_ptr(), cout, out.data_ptr(),
+                                         _stream()), "ewvit_stem_conv_fwd")
+    return out
+
+
+def dwconv3x3(x, w9c, bias, stride, out=None, pooled=None):
+    """Depthwise 3x3 + bias + SiLU on NHWC bf16; pooled (fp32 [n,c]) receives the spatial mean when given."""
+    _check_bf16(x, "x", 4)
+    _check_f32(w9c, "w9c")
+    n, h, wd, c = x.shape
+    bias = _f32_or_none(bias, "bias", c)
+    if out is None:
+        out = torch.empty((n, (h - 1) // stride + 1, (wd - 1) // stride + 1, c), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().ewvit_dwconv3x3_nhwc_bf16(x.data_ptr(), w9c.data_ptr(), bias.data_ptr(), n, h, wd, c, stride,
+                                               out.data_ptr(), _ptr(pooled), _stream()), "ewvit_dwconv3x3_nhwc_bf16")
+    return out
+
+
+def se_apply(x, pooled, w1, b1, w2t, b2):
+    """In-place squeeze-excitation scaling of NHWC bf16 x [n,h,w,c] from pooled [n,c]."""
+    _check_bf16(x, "x", 4)
+    n, h, wd, c = x.shape
+    sq = w1.shape[0]
+    for t, nm in ((pooled, "pooled"), (w1, "w1"), (b1, "b1"), (w2t, "w2t"), (b2, "b2")):
+        _check_f32(t, nm)
+    with torch.cuda.device(x.device):
+        check(load().ewvit_se_apply_nhwc_bf16(x.data_ptr(), pooled.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2t.data_ptr(),
+                                              b2.data_ptr(), n, h * wd, c, sq, _stream()), "ewvit_se_apply_nhwc_bf16")
+    return x

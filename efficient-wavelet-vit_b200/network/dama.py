@@ -87,8 +87,8 @@ class DAMA(NativeMixin, nn.Module):
         return {"fused": mix.mean(dim=[2, 3]), "space": space.mean(dim=[2, 3]), "freq": freq.mean(dim=[2, 3])}
 
     def _build_runner(self):
-        from ewvit.engine import DamaRunner, fused_bf16_backbone
-        backbone = fused_bf16_backbone(self.sfe.efficient_net.features, self.sfe.pos_embedding.device)
+        from ewvit.engine import DamaRunner, make_backbone
+        backbone = make_backbone(self.sfe.efficient_net.features, self.sfe.pos_embedding.device, v2s=True)
         sd = {k: v for k, v in self.state_dict().items() if not k.startswith("sfe.efficient_net.")}
         return DamaRunner(sd, self._config, backbone, dim=self.dim, heads=self.num_heads, levels=self.levels, depth=2)
 

@@ -37,8 +37,8 @@ class DeepfakeDetector(NativeMixin, nn.Module):
             yield x[:, start:min(start + self.batch_size, k)].flatten(0, 1)
 
     def _build_runner(self):
-        from ewvit.engine import DetectorRunner, fused_bf16_backbone
-        backbone = fused_bf16_backbone(self.dama.sfe.efficient_net.features, self.classifier[0].weight.device)
+        from ewvit.engine import DetectorRunner, make_backbone
+        backbone = make_backbone(self.dama.sfe.efficient_net.features, self.classifier[0].weight.device, v2s=True)
         sd = {k: v for k, v in self.state_dict().items()
               if (k.startswith("dama.") and not k.startswith("dama.sfe.efficient_net.")) or k.startswith("classifier.")}
         return DetectorRunner(sd, self.config, backbone, dim=self.dama_dim)

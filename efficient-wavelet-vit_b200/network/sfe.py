@@ -138,10 +138,10 @@ class EfficientViT(NativeMixin, nn.Module):
 
     # ---- native path
     def _build_runner(self):
-        from ewvit.engine import SfeRunner, fused_bf16_backbone
+        from ewvit.engine import SfeRunner, make_backbone
         feats = self.efficient_net.features if self.selected_efficient_net != 0 else _B0Features(self.efficient_net)
         dev = self.pos_embedding.device
-        backbone = fused_bf16_backbone(feats, dev)
+        backbone = make_backbone(feats, dev, v2s=self.selected_efficient_net != 0)
         sd = {k: v for k, v in self.state_dict().items() if not k.startswith("efficient_net.")}
         return SfeRunner(sd, self.config, backbone, "cls" if self.output_mode == "cls" else "feature_map")
 

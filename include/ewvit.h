@@ -198,6 +198,36 @@ EWVIT_API int ewvit_video_head_fwd(const float *fused, const float *space, const
                                    const float *cb1, const float *cw2, const float *cb2, int hc, float *logits,
                                    void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * EfficientNet feature extractor  (row a-6 / f-1; third-party arithmetic: torchvision `efficientnet_v2_s(...).features`
+ * called at reference network/sfe.py:150, eval mode, BatchNorm folded into weights/bias by the host)
+ * All activations NHWC bf16.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Dense NHWC convolution on the tcgen05 implicit-GEMM kernel with a fused epilogue:
+ *   y = act(conv(x, w) + bias) + residual          (the skip connection is added after the activation)
+ * ksize 1 (stride 1): w [cout, cin] bf16.   ksize 3 (pad 1, stride 1|2): w [cout, 9, cin_pad] bf16 with
+ * cin_pad = ceil(cin/64)*64 and zeros in the padding (k = tap*cin_pad + c).
+ *   x [n, h, wd, cin] bf16    y, residual [n, ho, wo, cout] bf16 (residual may be NULL)    bias [cout] fp32 or NULL
+ *   act: 0 none, 1 ReLU, 3 SiLU.    cin, cout multiples of 8 (tails are zero-filled by TMA and masked). */
+EWVIT_API int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, int wd, int cin, int cout, int ksize,
+                                   int stride, const float *bias, int act, const void *residual, void *y, void *stream);
+
+/* Stem: Conv2d(3 -> cout, 3x3, stride 2, pad 1) + bias + SiLU straight from the fp32 NCHW frames (also the
+ * fp32 -> bf16 / NCHW -> NHWC conversion).  x [n,3,h,wd] fp32, w [cout,3,3,3] fp32, y [n,ho,wo,cout] bf16. */
+EWVIT_API int ewvit_stem_conv_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
+                                  void *y, void *stream);
+
+/* Depthwise 3x3 (pad 1, stride 1|2) + bias + SiLU, plus the squeeze of the SE block: pooled[n, c] = spatial mean of
+ * the stored result (NULL to skip).  x [n,h,wd,c] bf16, w [9, c] fp32 (tap-major), y [n,ho,wo,c] bf16; c % 64 == 0. */
+EWVIT_API int ewvit_dwconv3x3_nhwc_bf16(const void *x, const float *w, const float *bias, int n, int h, int wd, int c,
+                                        int stride, void *y, float *pooled, void *stream);
+
+/* Squeeze-excitation (torchvision.ops.SqueezeExcitation with SiLU / Sigmoid): gate = sigmoid(W2 silu(W1 pooled + b1) + b2),
+ * x *= gate in place.  x [n,hw,c] bf16, pooled [n,c] fp32, w1 [sq,c], b1 [sq], w2t [sq,c] (= fc2 weight transposed), b2 [c]. */
+EWVIT_API int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const float *w1, const float *b1, const float *w2t,
+                                       const float *b2, int n, int hw, int c, int sq, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,120 @@
+"""GPU parity for the native EfficientNetV2-S feature extractor (row a-6 / f-1): each kernel against a plain fp32
+torch reference on the same bf16-rounded operands, then the whole extractor against torchvision's own fp32 module
+(the oracle's backbone) with the bf16 tolerance of tests/test_model_gpu.py."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _weights import seeded_randn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ewvit import ops
+    return ops
+
+
+def _close(got, ref, tol=2e-3, bf16_out=True):
+    err = (got.float().cpu() - ref).abs()
+    if bf16_out:
+        err = err - ref.abs() * 2.0 ** -8
+    lim = tol * float(ref.abs().max()) + 1e-6
+    assert float(err.max()) <= lim, f"max err {float(err.max())} > {lim}"
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("cin,cout,act,res", [(24, 48, None, False), (96, 48, None, True), (160, 960, "silu", False),
+                                              (1536, 256, None, True), (256, 1280, "silu", False), (64, 256, "silu", False)])
+def test_conv1x1(ops, cin, cout, act, res):
+    n, h, w = 3, 14, 10
+    x = seeded_randn((n, cin, h, w), 1).bfloat16()
+    wt = (seeded_randn((cout, cin, 1, 1), 2) * cin ** -0.5).bfloat16()
+    b = seeded_randn((cout,), 3)
+    r = seeded_randn((n, cout, h, w), 4).bfloat16() if res else None
+    ref = F.conv2d(x.float(), wt.float(), b)
+    if act == "silu":
+        ref = F.silu(ref)
+    if res:
+        ref = ref + r.float()
+    got = ops.conv_nhwc_bf16(_nhwc(x).cuda(), wt.flatten(1).contiguous().cuda(), 1, 1, bias=b.cuda(), act=act,
+                             residual=_nhwc(r).cuda() if res else None)
+    _close(got.permute(0, 3, 1, 2), ref)
+
+
+@pytest.mark.parametrize("cin,cout,stride,res,hw", [(24, 24, 1, True, (112, 112)), (24, 96, 2, False, (112, 112)),
+                                                   (48, 192, 1, False, (56, 56)), (64, 256, 1, False, (28, 28)),
+                                                   (48, 192, 2, False, (20, 12))])
+def test_conv3x3_small_channels(ops, cin, cout, stride, res, hw):
+    from ewvit import engine
+    n, (h, w) = 2, hw
+    x = seeded_randn((n, cin, h, w), 5).bfloat16()
+    wt = (seeded_randn((cout, cin, 3, 3), 6) * (9 * cin) ** -0.5).bfloat16()
+    b = seeded_randn((cout,), 7)
+    ref = F.silu(F.conv2d(x.float(), wt.float(), b, stride=stride, padding=1))
+    if res:
+        ref = ref + x.float()
+    wk = engine._w3x3_tapmajor_padded(wt.float()).cuda()
+    got = ops.conv_nhwc_bf16(_nhwc(x).cuda(), wk, 3, stride, bias=b.cuda(), act="silu", residual=_nhwc(x).cuda() if res else None)
+    _close(got.permute(0, 3, 1, 2), ref)
+
+
+def test_stem(ops):
+    x = seeded_randn((3, 3, 224, 224), 8)
+    wt = seeded_randn((24, 3, 3, 3), 9) * 27 ** -0.5
+    b = seeded_randn((24,), 10)
+    ref = F.silu(F.conv2d(x, wt, b, stride=2, padding=1))
+    got = ops.stem_conv(x.cuda(), wt.cuda().contiguous(), b.cuda())
+    assert got.shape == (3, 112, 112, 24)
+    _close(got.permute(0, 3, 1, 2), ref, tol=1e-4)
+
+
+@pytest.mark.parametrize("c,stride,hw", [(256, 2, (28, 28)), (960, 1, (14, 14)), (1536, 1, (7, 7)), (960, 2, (14, 14)), (64, 1, (5, 9))])
+def test_depthwise_and_squeeze(ops, c, stride, hw):
+    n, (h, w) = 3, hw
+    x = seeded_randn((n, c, h, w), 11).bfloat16()
+    wt = seeded_randn((c, 1, 3, 3), 12) * (1 / 3)
+    b = seeded_randn((c,), 13) * 0.1
+    ref = F.silu(F.conv2d(x.float(), wt, b, stride=stride, padding=1, groups=c))
+    pooled = torch.empty((n, c), device="cuda")
+    got = ops.dwconv3x3(_nhwc(x).cuda(), wt.reshape(c, 9).t().contiguous().cuda(), b.cuda(), stride, pooled=pooled)
+    _close(got.permute(0, 3, 1, 2), ref, tol=1e-4)
+    _close(pooled, ref.mean(dim=(2, 3)), tol=5e-3, bf16_out=False)
+
+
+def test_se_apply(ops):
+    n, c, sq, h, w = 4, 960, 40, 14, 14
+    x = seeded_randn((n, c, h, w), 14).bfloat16()
+    w1, b1 = seeded_randn((sq, c), 15) * c ** -0.5, seeded_randn((sq,), 16)
+    w2, b2 = seeded_randn((c, sq), 17) * sq ** -0.5, seeded_randn((c,), 18)
+    pooled = x.float().mean(dim=(2, 3))
+    gate = torch.sigmoid(F.silu(pooled @ w1.t() + b1) @ w2.t() + b2)
+    ref = x.float() * gate.view(n, c, 1, 1)
+    xd = _nhwc(x).cuda()
+    ops.se_apply(xd, pooled.cuda(), w1.cuda(), b1.cuda(), w2.t().contiguous().cuda(), b2.cuda())
+    _close(xd.permute(0, 3, 1, 2), ref, tol=1e-3)
+
+
+def test_native_backbone_matches_torchvision(dama_sd, golden):
+    from ewvit import engine
+    from oracle import ewvit_oracle as O
+    from torchvision.models import efficientnet_v2_s
+    frames = seeded_randn((2, 3, 224, 224), golden["frames_seed"])
+    net = efficientnet_v2_s(weights=None)
+    net.classifier = torch.nn.Identity()
+    p = "dama.sfe.efficient_net."
+    net.load_state_dict({k[len(p):]: v for k, v in dama_sd.items() if k.startswith(p)})
+    net.eval()
+    nb = engine.NativeEffNetV2(net.features, "cuda")
+    got = nb.forward(frames.cuda())
+    assert got.shape == (2, 7, 7, 1280) and got.dtype == torch.bfloat16
+    with torch.no_grad():
+        ref = O.backbone_v2s_features(dama_sd, p, frames)
+    e = float((got.float().cpu().permute(0, 3, 1, 2) - ref).abs().max() / ref.abs().max())
+    print(f"[parity] native EfficientNetV2-S features: max|err|/max|ref| = {e:.3e} (tol 6e-2)")
+    assert e <= 6e-2
+    assert torch.allclose(got.float().cpu().permute(0, 3, 1, 2).mean(dim=(2, 3)), golden["backbone_feat_mean"], atol=2e-2, rtol=5e-2)
