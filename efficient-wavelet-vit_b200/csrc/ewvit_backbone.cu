@@ -60,100 +60,120 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict_
 }
 
 // ---- depthwise 3x3 (stride 1|2, pad 1) + bias + SiLU, and the squeeze (spatial mean) of the result.
-//      One CTA owns all output pixels of (frame, channel slab of SC = 64 or 32 channels).  The slab's whole input
-//      plane is first staged in shared memory with coalesced 16-byte cp.async copies (<= ~50 KB, several CTAs per
-//      SM overlap their loads), then thread = (pixel lane, 8-channel group) reads its 9 taps from shared memory
-//      (LDS.128, a quarter-warp reads 128 contiguous bytes: conflict-free), and the squeeze needs no atomics.
+//      One CTA owns a channel slab (SC = 64 or 32 channels) of `fpc` consecutive frames.  Each frame's input plane
+//      for the slab is staged in shared memory with coalesced 16-byte cp.async copies, double-buffered so the next
+//      frame streams in while the current one is computed; thread = (pixel lane, 8-channel group) keeps its 72
+//      weights in registers for all frames and reads its 9 taps from shared memory (LDS.128, a quarter-warp reads
+//      128 contiguous bytes: conflict-free); the squeeze needs no atomics.
 template <int SC>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ x, const float *__restrict__ w,
                                                         const float *__restrict__ bias, __nv_bfloat16 *__restrict__ y,
-                                                        float *__restrict__ pooled, int h, int wd, int ho, int wo, int c,
-                                                        int stride) {
+                                                        float *__restrict__ pooled, int n, int h, int wd, int ho, int wo,
+                                                        int c, int stride, int fpc) {
     constexpr int G = SC / 8;            // 8-channel groups per slab
     constexpr int PL = 256 / G;          // pixel lanes
     extern __shared__ __align__(16) unsigned char dw_smem[];
-    __nv_bfloat16 *s_in = reinterpret_cast<__nv_bfloat16 *>(dw_smem);                  // [h*wd][SC]
-    float *s_w = reinterpret_cast<float *>(dw_smem + (size_t)h * wd * SC * 2);          // [9][SC] then bias [SC]
+    const int plane = h * wd * SC;                                                      // elements per stage
+    __nv_bfloat16 *s_in = reinterpret_cast<__nv_bfloat16 *>(dw_smem);                  // [2][h*wd][SC]
+    float *s_w = reinterpret_cast<float *>(dw_smem + (size_t)2 * plane * 2);            // [9][SC] then bias [SC]
     float *s_sum = s_w + 10 * SC;                                                       // [PL][SC + 1]
     const int slabs = c / SC;
-    const long long img = blockIdx.x / slabs;
     const int cs = (blockIdx.x % slabs) * SC;
+    const int f0 = (blockIdx.x / slabs) * fpc;
+    const int f1 = min(n, f0 + fpc);
     const int tid = threadIdx.x;
-    const __nv_bfloat16 *px = x + img * h * wd * c + cs;
-    for (int i = tid; i < h * wd * G; i += 256) {
-        const int p = i / G, g = i - p * G;
-        const uint32_t dst = ewvit::smem_u32(s_in + p * SC + g * 8);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(px + (long long)p * c + g * 8) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    auto stage_in = [&](int frame, int buf) {
+        const __nv_bfloat16 *px = x + (long long)frame * h * wd * c + cs;
+        __nv_bfloat16 *dstb = s_in + (size_t)buf * plane;
+        for (int i = tid; i < h * wd * G; i += 256) {
+            const int p = i / G, g = i - p * G;
+            const uint32_t dst = ewvit::smem_u32(dstb + p * SC + g * 8);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(px + (long long)p * c + g * 8) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage_in(f0, 0);
     for (int i = tid; i < 9 * SC; i += 256) s_w[i] = w[(i / SC) * c + cs + (i % SC)];
     if (tid < SC) s_w[9 * SC + tid] = bias[cs + tid];
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-
     const int g = tid % G, pl = tid / G;
-    float wr[9][8], br[8], sum[8];
+    float wr[9][8], br[8];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
         for (int j = 0; j < 8; ++j) wr[t][j] = s_w[t * SC + g * 8 + j];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { br[j] = s_w[9 * SC + g * 8 + j]; sum[j] = 0.f; }
-    __nv_bfloat16 *py = y + img * ho * wo * c + cs + g * 8;
-    for (int o = pl; o < ho * wo; o += PL) {
-        const int oy = o / wo, ox = o - oy * wo;
-        float a[8];
+    for (int j = 0; j < 8; ++j) br[j] = s_w[9 * SC + g * 8 + j];
+
+    for (int f = f0; f < f1; ++f) {
+        const int buf = (f - f0) & 1;
+        if (f + 1 < f1) {
+            stage_in(f + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const __nv_bfloat16 *sp = s_in + (size_t)buf * plane + g * 8;
+        __nv_bfloat16 *py = y + (long long)f * ho * wo * c + cs + g * 8;
+        float sum[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = br[j];
+        for (int j = 0; j < 8; ++j) sum[j] = 0.f;
+        for (int o = pl; o < ho * wo; o += PL) {
+            const int oy = o / wo, ox = o - oy * wo;
+            float a[8];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-            const int iy = oy * stride + dy - 1;
-            if (iy < 0 || iy >= h) continue;
+            for (int j = 0; j < 8; ++j) a[j] = br[j];
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                const int ix = ox * stride + dx - 1;
-                if (ix < 0 || ix >= wd) continue;
-                const uint4 v = *reinterpret_cast<const uint4 *>(s_in + (iy * wd + ix) * SC + g * 8);
-                const __nv_bfloat162 *vp = reinterpret_cast<const __nv_bfloat162 *>(&v);
+            for (int dy = 0; dy < 3; ++dy) {
+                const int iy = oy * stride + dy - 1;
+                if (iy < 0 || iy >= h) continue;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = __bfloat1622float2(vp[j]);
-                    a[2 * j] = fmaf(wr[dy * 3 + dx][2 * j], f.x, a[2 * j]);
-                    a[2 * j + 1] = fmaf(wr[dy * 3 + dx][2 * j + 1], f.y, a[2 * j + 1]);
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int ix = ox * stride + dx - 1;
+                    if (ix < 0 || ix >= wd) continue;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(sp + (iy * wd + ix) * SC);
+                    const __nv_bfloat162 *vp = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 fv = __bfloat1622float2(vp[j]);
+                        a[2 * j] = fmaf(wr[dy * 3 + dx][2 * j], fv.x, a[2 * j]);
+                        a[2 * j + 1] = fmaf(wr[dy * 3 + dx][2 * j + 1], fv.y, a[2 * j + 1]);
+                    }
                 }
             }
-        }
-        uint4 pk;
-        __nv_bfloat162 *pp = reinterpret_cast<__nv_bfloat162 *>(&pk);
+            uint4 pk;
+            __nv_bfloat162 *pp = reinterpret_cast<__nv_bfloat162 *>(&pk);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            pp[j] = __floats2bfloat162_rn(silu(a[2 * j]), silu(a[2 * j + 1]));
-            const float2 r = __bfloat1622float2(pp[j]);   // pool what is actually stored
-            sum[2 * j] += r.x;
-            sum[2 * j + 1] += r.y;
+            for (int j = 0; j < 4; ++j) {
+                pp[j] = __floats2bfloat162_rn(silu(a[2 * j]), silu(a[2 * j + 1]));
+                const float2 r = __bfloat1622float2(pp[j]);   // pool what is actually stored
+                sum[2 * j] += r.x;
+                sum[2 * j + 1] += r.y;
+            }
+            *reinterpret_cast<uint4 *>(py + (long long)o * c) = pk;
         }
-        *reinterpret_cast<uint4 *>(py + (long long)o * c) = pk;
-    }
-    if (pooled) {
+        if (pooled) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s_sum[pl * (SC + 1) + g * 8 + j] = sum[j];
-        __syncthreads();
-        if (tid < SC) {
-            float s = 0.f;
-            for (int i = 0; i < PL; ++i) s += s_sum[i * (SC + 1) + tid];
-            pooled[img * c + cs + tid] = s / (float)(ho * wo);
+            for (int j = 0; j < 8; ++j) s_sum[pl * (SC + 1) + g * 8 + j] = sum[j];
+            __syncthreads();
+            if (tid < SC) {
+                float s = 0.f;
+                for (int i = 0; i < PL; ++i) s += s_sum[i * (SC + 1) + tid];
+                pooled[(long long)f * c + cs + tid] = s / (float)(ho * wo);
+            }
         }
+        __syncthreads();   // everyone is done with this stage buffer (and s_sum) before it is refilled
     }
 }
 
-// ---- squeeze-excitation: gate = sigmoid(W2 * silu(W1 * pooled + b1) + b2), then x *= gate in place.
-//      grid = (frames, splits): every CTA recomputes the (tiny) gate of its frame and scales its share of pixels.
-__global__ void __launch_bounds__(256) se_apply_kernel(__nv_bfloat16 *__restrict__ x, const float *__restrict__ pooled,
-                                                       const float *__restrict__ w1, const float *__restrict__ b1,
-                                                       const float *__restrict__ w2t, const float *__restrict__ b2, int hw,
-                                                       int c, int sq) {
+// ---- squeeze-excitation gate: gate[n, c] = sigmoid(W2 * silu(W1 * pooled[n] + b1) + b2); one CTA per frame
+__global__ void __launch_bounds__(256) se_gate_kernel(const float *__restrict__ pooled, const float *__restrict__ w1,
+                                                      const float *__restrict__ b1, const float *__restrict__ w2t,
+                                                      const float *__restrict__ b2, float *__restrict__ gate, int c, int sq) {
     extern __shared__ float se_sm[];
-    float *s_pool = se_sm, *s_hid = se_sm + c, *s_gate = s_hid + sq;
+    float *s_pool = se_sm, *s_hid = se_sm + c;
     const long long img = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < c; i += 256) s_pool[i] = pooled[img * c + i];
@@ -169,25 +189,26 @@ __global__ void __launch_bounds__(256) se_apply_kernel(__nv_bfloat16 *__restrict
     for (int i = tid; i < c; i += 256) {
         float s = b2[i];
         for (int j = 0; j < sq; ++j) s = fmaf(w2t[(long long)j * c + i], s_hid[j], s);
-        s_gate[i] = 1.f / (1.f + __expf(-s));
+        gate[img * c + i] = 1.f / (1.f + __expf(-s));
     }
-    __syncthreads();
-    const int c8 = c / 8;
-    const long long per = ((long long)hw * c8 + gridDim.y - 1) / gridDim.y;
-    const long long lo = blockIdx.y * per, hi = min((long long)hw * c8, lo + per);
-    __nv_bfloat16 *px = x + img * hw * c;
-    for (long long i = lo + tid; i < hi; i += 256) {
+}
+
+// ---- x[n, hw, c] *= gate[n, c] in place, 8 channels (16 bytes) per thread
+__global__ void __launch_bounds__(256) se_scale_kernel(__nv_bfloat16 *__restrict__ x, const float *__restrict__ gate,
+                                                       long long total8, int hw, int c8) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total8; i += (long long)gridDim.x * 256) {
         const int cg = (int)(i % c8);
-        uint4 v = *reinterpret_cast<uint4 *>(px + i * 8);
+        const long long img = i / ((long long)hw * c8);
+        uint4 v = *reinterpret_cast<uint4 *>(x + i * 8);
+        const float4 g0 = *reinterpret_cast<const float4 *>(gate + (img * c8 + cg) * 8);
+        const float4 g1 = *reinterpret_cast<const float4 *>(gate + (img * c8 + cg) * 8 + 4);
         __nv_bfloat162 *vp = reinterpret_cast<__nv_bfloat162 *>(&v);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float2 f = __bfloat1622float2(vp[j]);
-            f.x *= s_gate[cg * 8 + 2 * j];
-            f.y *= s_gate[cg * 8 + 2 * j + 1];
-            vp[j] = __floats2bfloat162_rn(f.x, f.y);
-        }
-        *reinterpret_cast<uint4 *>(px + i * 8) = v;
+        float2 f;
+        f = __bfloat1622float2(vp[0]); vp[0] = __floats2bfloat162_rn(f.x * g0.x, f.y * g0.y);
+        f = __bfloat1622float2(vp[1]); vp[1] = __floats2bfloat162_rn(f.x * g0.z, f.y * g0.w);
+        f = __bfloat1622float2(vp[2]); vp[2] = __floats2bfloat162_rn(f.x * g1.x, f.y * g1.y);
+        f = __bfloat1622float2(vp[3]); vp[3] = __floats2bfloat162_rn(f.x * g1.z, f.y * g1.w);
+        *reinterpret_cast<uint4 *>(x + i * 8) = v;
     }
 }
 
@@ -223,9 +244,9 @@ extern "C" int ewvit_dwconv3x3_nhwc_bf16(const void *x, const float *w, const fl
     if (rc != EWVIT_OK) return rc;
     const int ho = (h - 1) / stride + 1, wo = (wd - 1) / stride + 1;
     // 64-channel slabs when the staged input plane fits ~56 KB of shared memory, else 32-channel slabs
-    const bool wide = (size_t)h * wd * 64 * 2 <= 56 * 1024;
+    const bool wide = (size_t)h * wd * 64 * 2 <= 50 * 1024;   // two stages of the slab's input plane
     const int sc = wide ? 64 : 32;
-    const size_t smem = (size_t)h * wd * sc * 2 + (size_t)10 * sc * 4 + (size_t)(256 / (sc / 8)) * (sc + 1) * 4;
+    const size_t smem = (size_t)2 * h * wd * sc * 2 + (size_t)10 * sc * 4 + (size_t)(256 / (sc / 8)) * (sc + 1) * 4;
     EWVIT_REQUIRE(smem <= 200 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_dwconv3x3_nhwc_bf16: %dx%d input plane too large for the staged kernel", h, wd);
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -235,29 +256,36 @@ extern "C" int ewvit_dwconv3x3_nhwc_bf16(const void *x, const float *w, const fl
         EWVIT_CUDA_OK(cudaFuncSetAttribute(dwconv3x3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    const unsigned grid = (unsigned)((long long)n * (c / sc));
+    // frames per CTA: amortise the weight prologue while keeping >= ~4 CTAs per SM in the grid
+    int fpc = 8;
+    while (fpc > 1 && (long long)((n + fpc - 1) / fpc) * (c / sc) < 4LL * ewvit_num_sms()) fpc /= 2;
+    const unsigned grid = (unsigned)((long long)((n + fpc - 1) / fpc) * (c / sc));
     if (wide)
         dwconv3x3_kernel<64><<<grid, 256, smem, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16 *>(x), w, bias,
-                                                                        static_cast<__nv_bfloat16 *>(y), pooled, h, wd, ho, wo, c, stride);
+                                                                        static_cast<__nv_bfloat16 *>(y), pooled, n, h, wd, ho, wo, c, stride, fpc);
     else
         dwconv3x3_kernel<32><<<grid, 256, smem, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16 *>(x), w, bias,
-                                                                        static_cast<__nv_bfloat16 *>(y), pooled, h, wd, ho, wo, c, stride);
+                                                                        static_cast<__nv_bfloat16 *>(y), pooled, n, h, wd, ho, wo, c, stride, fpc);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }
 
 extern "C" int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const float *w1, const float *b1, const float *w2t,
-                                        const float *b2, int n, int hw, int c, int sq, void *stream) {
+                                        const float *b2, int n, int hw, int c, int sq, float *gate_ws, void *stream) {
     EWVIT_REQUIRE(n >= 0 && hw > 0 && c > 0 && sq > 0, EWVIT_ERR_INVALID_ARG, "ewvit_se_apply_nhwc_bf16: bad sizes");
     if (n == 0) return EWVIT_OK;
-    EWVIT_REQUIRE(x && pooled && w1 && b1 && w2t && b2 && ewvit_aligned16(x), EWVIT_ERR_INVALID_ARG,
+    EWVIT_REQUIRE(x && pooled && w1 && b1 && w2t && b2 && gate_ws && ewvit_aligned16(x) && ewvit_aligned16(gate_ws), EWVIT_ERR_INVALID_ARG,
                   "ewvit_se_apply_nhwc_bf16: NULL or misaligned pointer");
-    EWVIT_REQUIRE(c % 8 == 0 && (2 * c + sq) * 4 <= 48 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_se_apply_nhwc_bf16: c=%d sq=%d not supported", c, sq);
+    EWVIT_REQUIRE(c % 8 == 0 && (c + sq) * 4 <= 48 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_se_apply_nhwc_bf16: c=%d sq=%d not supported", c, sq);
     int rc = ewvit_check_device();
     if (rc != EWVIT_OK) return rc;
-    const int splits = hw >= 100 ? 4 : 2;
-    se_apply_kernel<<<dim3(n, splits), 256, (2 * c + sq) * sizeof(float), (cudaStream_t)stream>>>(
-        static_cast<__nv_bfloat16 *>(x), pooled, w1, b1, w2t, b2, hw, c, sq);
+    se_gate_kernel<<<(unsigned)n, 256, (c + sq) * sizeof(float), (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, gate_ws, c, sq);
+    EWVIT_LAUNCH_OK();
+    const long long total8 = (long long)n * hw * (c / 8);
+    long long blocks = (total8 + 255) / 256;
+    const long long cap = (long long)ewvit_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    se_scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(static_cast<__nv_bfloat16 *>(x), gate_ws, total8, hw, c / 8);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }

@@ -15,7 +15,7 @@ ewvit_encode_tiled_fn ewvit_get_encode_tiled();
 // bf16 tensor, `rank` dims (innermost first), 128-byte swizzle, zero OOB fill.
 // dims[i] elements, strides_bytes[i] for i>=1 (stride of dim 0 is the element size), box[i], estr[i].
 int ewvit_make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t *dims,
-                         const uint64_t *strides_bytes, const uint32_t *box, const uint32_t *estr);
+                         const uint64_t *strides_bytes, const uint32_t *box, const uint32_t *estr, bool swizzle128 = true);
 
 #ifdef __CUDACC__
 namespace ewvit {

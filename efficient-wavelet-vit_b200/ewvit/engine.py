@@ -208,11 +208,13 @@ def _fold_conv_bn(conv, bn):
 
 
 def _w3x3_tapmajor_padded(w):
-    """[cout, cin, 3, 3] fp32 -> bf16 [cout, 9, ceil(cin/64)*64] with zero padding (layout of ewvit_conv_nhwc_bf16)."""
+    """[cout, cin, 3, 3] fp32 -> bf16 [cout, Kpad]: dense k = (ky*3+kx)*cin + c, zero-padded to a multiple of 64
+    (layout of ewvit_conv_nhwc_bf16)."""
     cout, cin = w.shape[:2]
-    cpad = (cin + 63) // 64 * 64
-    out = torch.zeros((cout, 9, cpad), dtype=torch.bfloat16, device=w.device)
-    out[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin).to(torch.bfloat16)
+    k = 9 * cin
+    kpad = (k + 63) // 64 * 64
+    out = torch.zeros((cout, kpad), dtype=torch.bfloat16, device=w.device)
+    out[:, :k] = w.permute(0, 2, 3, 1).reshape(cout, k).to(torch.bfloat16)
     return out.contiguous()
 
 

@@ -329,14 +329,17 @@ def dwconv3x3(x, w9c, bias, stride, out=None, pooled=None):
     return out
 
 
-def se_apply(x, pooled, w1, b1, w2t, b2):
+def se_apply(x, pooled, w1, b1, w2t, b2, gate_ws=None):
     """In-place squeeze-excitation scaling of NHWC bf16 x [n,h,w,c] from pooled [n,c]."""
     _check_bf16(x, "x", 4)
     n, h, wd, c = x.shape
     sq = w1.shape[0]
     for t, nm in ((pooled, "pooled"), (w1, "w1"), (b1, "b1"), (w2t, "w2t"), (b2, "b2")):
         _check_f32(t, nm)
+    if gate_ws is None:
+        gate_ws = torch.empty((n, c), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         check(load().ewvit_se_apply_nhwc_bf16(x.data_ptr(), pooled.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2t.data_ptr(),
-                                              b2.data_ptr(), n, h * wd, c, sq, _stream()), "ewvit_se_apply_nhwc_bf16")
+                                              b2.data_ptr(), n, h * wd, c, sq, gate_ws.data_ptr(), _stream()),
+              "ewvit_se_apply_nhwc_bf16")
     return x

@@ -206,8 +206,8 @@ EWVIT_API int ewvit_video_head_fwd(const float *fused, const float *space, const
 
 /* Dense NHWC convolution on the tcgen05 implicit-GEMM kernel with a fused epilogue:
  *   y = act(conv(x, w) + bias) + residual          (the skip connection is added after the activation)
- * ksize 1 (stride 1): w [cout, cin] bf16.   ksize 3 (pad 1, stride 1|2): w [cout, 9, cin_pad] bf16 with
- * cin_pad = ceil(cin/64)*64 and zeros in the padding (k = tap*cin_pad + c).
+ * ksize 1 (stride 1): w [cout, cin] bf16.   ksize 3 (pad 1, stride 1|2; cin <= 64 or cin % 64 == 0):
+ * w [cout, Kpad] bf16 with the dense tap-major index k = (ky*3+kx)*cin + c, zero-padded to Kpad = ceil(9*cin/64)*64.
  *   x [n, h, wd, cin] bf16    y, residual [n, ho, wo, cout] bf16 (residual may be NULL)    bias [cout] fp32 or NULL
  *   act: 0 none, 1 ReLU, 3 SiLU.    cin, cout multiples of 8 (tails are zero-filled by TMA and masked). */
 EWVIT_API int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, int wd, int cin, int cout, int ksize,
@@ -224,9 +224,14 @@ EWVIT_API int ewvit_dwconv3x3_nhwc_bf16(const void *x, const float *w, const flo
                                         int stride, void *y, float *pooled, void *stream);
 
 /* Squeeze-excitation (torchvision.ops.SqueezeExcitation with SiLU / Sigmoid): gate = sigmoid(W2 silu(W1 pooled + b1) + b2),
- * x *= gate in place.  x [n,hw,c] bf16, pooled [n,c] fp32, w1 [sq,c], b1 [sq], w2t [sq,c] (= fc2 weight transposed), b2 [c]. */
+ * x *= gate in place.  x [n,hw,c] bf16, pooled [n,c] fp32, w1 [sq,c], b1 [sq], w2t [sq,c] (= fc2 weight transposed), b2 [c],
+ * gate_ws [n,c] fp32 workspace (receives the gate). */
 EWVIT_API int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const float *w1, const float *b1, const float *w2t,
-                                       const float *b2, int n, int hw, int c, int sq, void *stream);
+                                       const float *b2, int n, int hw, int c, int sq, float *gate_ws, void *stream);
+
+/* Debug aid for kernel bring-up: when non-NULL, CTA 0 of every subsequent tensor-core GEMM/conv launch writes
+ * clock64 stamps of its warp roles to this device buffer ([4 roles][64 tiles][4] int64).  NULL switches it off. */
+EWVIT_API int ewvit_debug_set_trace(void *device_buffer);
 
 #ifdef __cplusplus
 }
