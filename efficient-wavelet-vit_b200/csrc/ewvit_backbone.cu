@@ -8,7 +8,7 @@
 
 namespace {
 
-__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return ewvit::silu_fast(x); }
 
 // ---- stem: Conv2d(3 -> cout<=32, 3x3, stride 2, pad 1) + bias + SiLU, fp32 NCHW frames -> bf16 NHWC
 //      (also the fp32 -> bf16 conversion of the input; torchvision features[0], sfe.py:150)

@@ -125,6 +125,15 @@ __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+// SiLU with ONE special-function op: x*sigmoid(x) = 0.5x*tanh(0.5x) + 0.5x (MUFU.TANH; the exp+rcp form needs two and
+// made the short-K conv epilogues MUFU-bound).  |rel err| ~ 2^-11, far below the bf16 rounding of the stored value.
+__device__ __forceinline__ float silu_fast(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(

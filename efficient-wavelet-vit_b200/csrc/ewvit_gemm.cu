@@ -28,15 +28,13 @@ constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int kStages = 6;
 constexpr int kAccStages = 2;
 constexpr int kTileBytes = BM * BK * 2;        // 16 KiB
-constexpr int kStageBytes = 2 * kTileBytes;    // A + B
 constexpr int kEpiWarps = 8;                   // 2 warps per TMEM lane quarter, each takes half the columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;  // 320
 enum { EPI_CONV = 0, EPI_LINEAR = 1, EPI_PARTIAL = 2, EPI_BB = 3 };
-constexpr uint32_t kTmemCols = kAccStages * BN;   // 256
 constexpr int kBuilderWarps = 4;                // A_IM2COL only: 128 threads assemble the A tiles in shared memory
 constexpr int kThreadsBuilder = kThreads + 32 * kBuilderWarps;   // 448
 constexpr int kMaxHalo = 8;                     // A_IM2COL: halo ring depth (TMA latency of the small-row boxes is ~3 us)
-constexpr int kPayloadBytes = 222 * 1024;       // operand stages (+ halo buffers); barriers live right behind
+constexpr int kPayloadBytes = 220 * 1024;       // operand stages (+ halo buffers); barriers live right behind
 constexpr int kSmemBytes = kPayloadBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 
 enum { A_FLAT = 0, A_TILE4D = 1, A_IM2COL = 2 };
@@ -92,7 +90,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
         if (p.trace && blockIdx.x == 0 && (tile) < 64) p.trace[((role) * 64 + (tile)) * 4 + (k)] = clock64(); \
     } while (0)
 
-template <int kEpi, bool kBuilder>
+template <int kEpi, bool kBuilder, int kBN>
 __global__ void __launch_bounds__(kBuilder ? kThreadsBuilder : kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ unsigned char smem_dyn[];
@@ -102,7 +100,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                        *tempty = bars + 2 * kStages + kAccStages;
     unsigned long long *hfull = bars + 2 * kStages + 2 * kAccStages, *hempty = hfull + kMaxHalo;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(hempty + kMaxHalo);
-    __shared__ __align__(16) float s_scale[2 * BN], s_shift[2 * BN];
+    constexpr int kStageB = kTileBytes + kBN * BK * 2;   // A tile + B tile of this column width
+    constexpr uint32_t kTmemColsT = kAccStages * kBN;
+    __shared__ __align__(16) float s_scale[2 * kBN], s_shift[2 * kBN];
     __shared__ int s_koff[kBuilder ? 9 * 8 : 1];
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler, too
@@ -127,7 +127,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ewvit::mbar_fence_init();
     }
     if (warp == 1) {
-        ewvit::tmem_alloc(ewvit::smem_u32(tmem_slot), kTmemCols);
+        ewvit::tmem_alloc(ewvit::smem_u32(tmem_slot), kTmemColsT);
         ewvit::tmem_relinquish();
     }
     ewvit::tc_fence_before();
@@ -166,7 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // the tile's input halo (out-of-image pixels zero-filled) as a few wide boxes; then only B per k-block
                 ewvit::mbar_wait(ewvit::smem_u32(&hempty[hb]), hphase ^ 1);
                 const uint32_t hbar = ewvit::smem_u32(&hfull[hb]);
-                const uint32_t hdst = smem_base + nstages * kStageBytes + hb * p.halo_stride;
+                const uint32_t hdst = smem_base + nstages * kStageB + hb * p.halo_stride;
                 const int hx0 = (tx * p.box_w * p.in_stride - 1) * p.cin, hy0 = ty * p.box_h * p.in_stride - 1;
                 if (ewvit::elect_one()) {
                     ewvit::mbar_expect_tx(hbar, (uint32_t)p.halo_bytes);
@@ -178,10 +178,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ewvit::mbar_wait(ewvit::smem_u32(&empty[stage]), phase ^ 1);
                     const uint32_t bar = ewvit::smem_u32(&full[stage]);
-                    const uint32_t b_dst = smem_base + stage * kStageBytes + kTileBytes;
+                    const uint32_t b_dst = smem_base + stage * kStageB + kTileBytes;
                     if (ewvit::elect_one()) {
-                        ewvit::mbar_expect_tx(bar, kTileBytes);
-                        ewvit::tma_load_2d(b_dst, &tmB, kb * BK, n_t * BN, bar);
+                        ewvit::mbar_expect_tx(bar, kBN * BK * 2);
+                        ewvit::tma_load_2d(b_dst, &tmB, kb * BK, n_t * kBN, bar);
                     }
                     __syncwarp();
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -194,14 +194,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = kb0; kb < kb1; ++kb) {
                 ewvit::mbar_wait(ewvit::smem_u32(&empty[stage]), phase ^ 1);
                 const uint32_t bar = ewvit::smem_u32(&full[stage]);
-                const uint32_t a_dst = smem_base + stage * kStageBytes;
+                const uint32_t a_dst = smem_base + stage * kStageB;
                 if (ewvit::elect_one()) {
-                    ewvit::mbar_expect_tx(bar, kStageBytes);
+                    ewvit::mbar_expect_tx(bar, kStageB);
                     if (p.a_mode == A_FLAT)
                         ewvit::tma_load_2d(a_dst, &tmA, chunk * BK, m_t * BM + p.tap_a0[tap], bar);
                     else
                         ewvit::tma_load_4d(a_dst, &tmA, chunk * BK, ax0 + p.tap_a0[tap], ay0 + p.tap_a1[tap], img, bar);
-                    ewvit::tma_load_2d(a_dst + kTileBytes, &tmB, kb * BK, n_t * BN, bar);
+                    ewvit::tma_load_2d(a_dst + kTileBytes, &tmB, kb * BK, n_t * kBN, bar);
                 }
                 __syncwarp();
                 if (++chunk == p.chunks_per_tap) { chunk = 0; ++tap; }
@@ -223,17 +223,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int kb0 = sp * p.kb_per_split;
             const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             // columns past N are zero-filled B rows: shrink the MMA's N to the valid part (multiple of 16)
-            const int n_valid = min(BN, p.N - (wn % p.tiles_n) * BN);
+            const int n_valid = min(kBN, p.N - (wn % p.tiles_n) * kBN);
             const uint32_t idesc = ewvit::umma_idesc_bf16(BM, (uint32_t)((n_valid + 15) & ~15));
             ewvit::mbar_wait(ewvit::smem_u32(&tempty[acc]), acc_phase ^ 1);
             ewvit::tc_fence_after();
             if (lane == 0) EWVIT_TRACE(1, tt, 1);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kBN);
             for (int kb = kb0; kb < kb1; ++kb) {
                 ewvit::mbar_wait(ewvit::smem_u32(&full[stage]), phase);
                 if (kb == kb0 && lane == 0) EWVIT_TRACE(1, tt, 2);
                 ewvit::tc_fence_after();
-                const uint32_t a_addr = smem_base + stage * kStageBytes;
+                const uint32_t a_addr = smem_base + stage * kStageB;
                 const uint64_t a_desc = ewvit::umma_desc_sw128(a_addr), b_desc = ewvit::umma_desc_sw128(a_addr + kTileBytes);
                 const uint32_t ebar = ewvit::smem_u32(&empty[stage]);
                 const uint32_t first = kb > kb0 ? 1u : 0u;
@@ -296,13 +296,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int kb0 = sp * p.kb_per_split;
             const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             ewvit::mbar_wait(ewvit::smem_u32(&hfull[hb]), hphase);
-            const uint32_t halo = smem_base + nstages * kStageBytes + hb * p.halo_stride;
+            const uint32_t halo = smem_base + nstages * kStageB + hb * p.halo_stride;
             for (int kb = kb0; kb < kb1; ++kb, ++g) {
-                if ((int)(g & (kBuilderWarps - 1)) != bwarp) continue;
+                // every ring slot is owned by ONE builder warp, so consecutive uses of a slot are ordered by that warp's
+                // own waits (two warps sharing a slot could run two phases apart, which a parity wait cannot see)
                 const int stage = (int)(g % (uint32_t)nstages);
+                if ((stage & (kBuilderWarps - 1)) != bwarp) continue;
                 const uint32_t phase = (g / (uint32_t)nstages) & 1u;
                 ewvit::mbar_wait(ewvit::smem_u32(&empty[stage]), phase ^ 1);
-                const uint32_t a_base = smem_base + stage * kStageBytes;
+                const uint32_t a_base = smem_base + stage * kStageB;
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {
                     uint4 v[8];
@@ -339,7 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                 // other tile of this CTA, so two tiles are in flight in the epilogue
         const int r = q * 32 + lane;            // row of the tile owned by this thread
         const int gtid = (threadIdx.x - 64) & 127;
-        float *g_scale = s_scale + grp * BN, *g_shift = s_shift + grp * BN;
+        float *g_scale = s_scale + grp * kBN, *g_shift = s_shift + grp * kBN;
         const int acc = grp;
         uint32_t acc_phase = 0;
         int cur_nt = -1;
@@ -354,10 +356,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
             if ((kEpi == EPI_CONV || kEpi == EPI_BB) && n_t != cur_nt) {   // (re)stage the per-channel scale/shift of this column tile
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-                {
-                    const bool in = n_t * BN + gtid < p.N;
-                    g_scale[gtid] = (p.scale && in) ? p.scale[n_t * BN + gtid] : 1.f;
-                    g_shift[gtid] = (p.shift && in) ? p.shift[n_t * BN + gtid] : 0.f;
+                for (int i = gtid; i < kBN; i += 128) {
+                    const bool in = n_t * kBN + i < p.N;
+                    g_scale[i] = (p.scale && in) ? p.scale[n_t * kBN + i] : 1.f;
+                    g_shift[i] = (p.shift && in) ? p.shift[n_t * kBN + i] : 0.f;
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                 cur_nt = n_t;
@@ -383,22 +385,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 orow = (long long)img * p.out_img_rows + (long long)(oy + p.out_pad) * p.out_wp + ox + p.out_pad;
             }
             if (kEpi == EPI_BB && p.residual_bf16 && valid) {   // start pulling the skip-connection row while the MMAs run
-                const __nv_bfloat16 *rp = p.residual_bf16 + orow * p.ldr + n_t * BN;
-                const int ncol = min(BN, p.N - n_t * BN);
+                const __nv_bfloat16 *rp = p.residual_bf16 + orow * p.ldr + n_t * kBN;
+                const int ncol = min(kBN, p.N - n_t * kBN);
                 for (int cb = 0; cb < ncol; cb += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + cb));
             }
 
             ewvit::mbar_wait(ewvit::smem_u32(&tfull[acc]), acc_phase);
             ewvit::tc_fence_after();
             if (q == 2 && lane == 0) EWVIT_TRACE(2 + grp, it, 1);
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kBN);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                if (kEpi == EPI_BB && n_t * BN + c * 32 >= p.N) continue;   // warp-uniform: nothing valid in this chunk
+            for (int c = 0; c < kBN / 32; ++c) {
+                if (kEpi == EPI_BB && n_t * kBN + c * 32 >= p.N) continue;   // warp-uniform: nothing valid in this chunk
                 uint32_t v[32];
                 ewvit::tmem_ld_32x32(t_row + c * 32, v);
                 ewvit::tmem_ld_wait();
-                const int col0 = n_t * BN + c * 32;
+                const int col0 = n_t * kBN + c * 32;
                 if (!valid) continue;
                 if (kEpi == EPI_BB) {
                     // bias (+ SiLU / ReLU) (+ bf16 residual) -> bf16, 8 columns (16 bytes) at a time, masked past N
@@ -412,7 +414,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int i = 0; i < 8; ++i) f8[i] = __uint_as_float(v[g8 * 8 + i]) + g_shift[c * 32 + g8 * 8 + i];
                         if (p.act == 3) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) f8[i] = __fdividef(f8[i], 1.f + __expf(-f8[i]));
+                            for (int i = 0; i < 8; ++i) f8[i] = ewvit::silu_fast(f8[i]);
                         } else if (p.act == 1) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) f8[i] = fmaxf(f8[i], 0.f);
@@ -508,7 +510,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     ewvit::tc_fence_before();
     __syncthreads();
-    if (warp == 1) ewvit::tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == 1) ewvit::tmem_dealloc(tmem_base, kTmemColsT);
 }
 
 // Split-K second pass: sum the fp32 partials, then the same epilogue as the fused path.
@@ -548,34 +550,35 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ partial, int spli
 
 static long long *g_trace = nullptr;
 
-template <int kEpi, bool kBuilder>
+template <int kEpi, bool kBuilder, int kBN>
 int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams p, cudaStream_t stream) {
     static bool attr_set[64] = {false};
     int dev = 0;
     EWVIT_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        EWVIT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kBuilder>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kBuilder, kBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    if (p.stages <= 0) p.stages = kStages;
+    if (p.stages <= 0) p.stages = kBN == 128 ? kStages : kPayloadBytes / (kTileBytes + kBN * BK * 2);
     p.trace = g_trace;
     long long work = (long long)p.tiles_m * p.tiles_n * p.splits;
     long long grid = ewvit_num_sms();
     if (grid > work) grid = work;
     if (grid <= 0) return EWVIT_OK;
-    gemm_tc_kernel<kEpi, kBuilder><<<(unsigned)grid, kBuilder ? kThreadsBuilder : kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+    gemm_tc_kernel<kEpi, kBuilder, kBN><<<(unsigned)grid, kBuilder ? kThreadsBuilder : kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }
 
-int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int epi, cudaStream_t stream) {
-    if (epi == EPI_CONV) return launch_gemm_t<EPI_CONV, false>(tmA, tmB, p, stream);
+int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int epi, cudaStream_t stream, int bn = BN) {
+    if (epi == EPI_CONV) return launch_gemm_t<EPI_CONV, false, 128>(tmA, tmB, p, stream);
     if (epi == EPI_BB) {
-        if (p.a_mode == A_IM2COL) return launch_gemm_t<EPI_BB, true>(tmA, tmB, p, stream);
-        return launch_gemm_t<EPI_BB, false>(tmA, tmB, p, stream);
+        if (p.a_mode == A_IM2COL)
+            return bn == 256 ? launch_gemm_t<EPI_BB, true, 256>(tmA, tmB, p, stream) : launch_gemm_t<EPI_BB, true, 128>(tmA, tmB, p, stream);
+        return bn == 256 ? launch_gemm_t<EPI_BB, false, 256>(tmA, tmB, p, stream) : launch_gemm_t<EPI_BB, false, 128>(tmA, tmB, p, stream);
     }
-    if (epi == EPI_PARTIAL) return launch_gemm_t<EPI_PARTIAL, false>(tmA, tmB, p, stream);
-    return launch_gemm_t<EPI_LINEAR, false>(tmA, tmB, p, stream);
+    if (epi == EPI_PARTIAL) return launch_gemm_t<EPI_PARTIAL, false, 128>(tmA, tmB, p, stream);
+    return launch_gemm_t<EPI_LINEAR, false, 128>(tmA, tmB, p, stream);
 }
 
 }  // namespace
@@ -772,8 +775,11 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
 
     const int ho = (h - 1) / stride + 1, wo = (wd - 1) / stride + 1;
     GemmParams p = {};
+    // column tile: 256 wide when cout > 128, so A is fetched (or assembled) once per 256 output channels
+    const int bn = cout > 128 ? 256 : 128;
+    const int stage_bytes = kTileBytes + bn * BK * 2;
     p.N = cout;
-    p.tiles_n = (cout + BN - 1) / BN;
+    p.tiles_n = (cout + bn - 1) / bn;
     p.splits = 1;
     p.out = y; p.out_fp32 = 0; p.ldo = cout; p.col_off = 0;
     p.shift = bias; p.act = act;
@@ -788,7 +794,7 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
         rc = ewvit_make_tmap_bf16(&tmA, x, 2, dims, str, box, nullptr);
         if (rc != EWVIT_OK) return rc;
         uint64_t dimsb[2] = {(uint64_t)cin, (uint64_t)cout};
-        uint32_t boxb[2] = {BK, BN};
+        uint32_t boxb[2] = {BK, (uint32_t)bn};
         rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, str, boxb, nullptr);
         if (rc != EWVIT_OK) return rc;
         p.a_mode = A_FLAT;
@@ -803,7 +809,7 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
         const int kdense = 9 * cin;
         const int num_kb = (kdense + BK - 1) / BK;
         uint64_t dimsb[2] = {(uint64_t)num_kb * BK, (uint64_t)cout}, strb[2] = {2, (uint64_t)num_kb * BK * 2};
-        uint32_t boxb[2] = {BK, BN};
+        uint32_t boxb[2] = {BK, (uint32_t)bn};
         rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, strb, boxb, nullptr);
         if (rc != EWVIT_OK) return rc;
         const int box_w = 16, box_h = 8;
@@ -832,9 +838,9 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
             p.plane_bytes = (plane_payload + 127) & ~127;                // TMA destinations must be 128-byte aligned
             p.halo_bytes = p.halo_nb * plane_payload;                   // bytes the TMA unit reports on the mbarrier
             p.halo_stride = (p.halo_nb * p.plane_bytes + 1023) & ~1023;
-            p.stages = 4;
-            if ((kPayloadBytes - p.stages * kStageBytes) / p.halo_stride < 2) p.stages = 3;
-            p.halo_bufs = (kPayloadBytes - p.stages * kStageBytes) / p.halo_stride;
+            p.stages = bn == 256 ? 3 : 4;
+            if ((kPayloadBytes - p.stages * stage_bytes) / p.halo_stride < 2) p.stages -= 1;
+            p.halo_bufs = (kPayloadBytes - p.stages * stage_bytes) / p.halo_stride;
             if (p.halo_bufs > kMaxHalo) p.halo_bufs = kMaxHalo;
             EWVIT_REQUIRE(p.halo_bufs >= 2, EWVIT_ERR_UNSUPPORTED, "ewvit_conv_nhwc_bf16: halo too large");
             p.chunks_per_tap = 1;
@@ -858,7 +864,7 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
                 }
         }
     }
-    return launch_gemm(tmA, tmB, p, EPI_BB, (cudaStream_t)stream);
+    return launch_gemm(tmA, tmB, p, EPI_BB, (cudaStream_t)stream, bn);
 }
 
 // Debug aid: when non-NULL, CTA 0 of every subsequent GEMM/conv launch writes clock64 stamps of its warp roles

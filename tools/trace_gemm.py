@@ -40,7 +40,7 @@ x = torch.randn(n, 112, 112, 24, device="cuda").bfloat16()
 w = engine._w3x3_tapmajor_padded(torch.randn(24, 24, 3, 3) * 0.07).cuda()
 b = torch.zeros(24, device="cuda")
 run("conv3 24->24 @112 (im2col, 4 kb/tile)", lambda: ops.conv_nhwc_bf16(x, w, 3, 1, bias=b, act="silu", residual=x))
-x2 = torch.randn(n, 14, 14, 160, device="cuda").bfloat16()
+x2 = torch.randn(512, 14, 14, 160, device="cuda").bfloat16()
 w2 = (torch.randn(960, 160, device="cuda") * 0.08).bfloat16()
 b2 = torch.zeros(960, device="cuda")
 run("conv1 160->960 @14 (3 kb/tile)", lambda: ops.conv_nhwc_bf16(x2, w2, 1, 1, bias=b2, act="silu"))
@@ -49,3 +49,9 @@ wh = (torch.randn(128, 3, 3, 64, device="cuda") * 0.04).bfloat16()
 yh = torch.empty(n, 114, 114, 128, device="cuda", dtype=torch.bfloat16)
 sc, sh = torch.ones(128, device="cuda"), torch.zeros(128, device="cuda")
 run("hf_fusion 64->128 @112 (9 kb/tile)", lambda: ops.conv3x3_bf16(xh, wh, n, 112, 112, 1, True, sc, sh, True, yh, 0, True))
+
+x3 = torch.randn(512, 14, 14, 960, device="cuda").bfloat16()
+w3 = (torch.randn(160, 960, device="cuda") * 0.03).bfloat16()
+b3 = torch.zeros(160, device="cuda")
+r3 = torch.randn(512, 14, 14, 160, device="cuda").bfloat16()
+run("conv1 960->160 @14 project + residual (15 kb/tile)", lambda: ops.conv_nhwc_bf16(x3, w3, 1, 1, bias=b3, act=None, residual=r3))
