@@ -34,7 +34,10 @@ enum { EPI_CONV = 0, EPI_LINEAR = 1, EPI_PARTIAL = 2, EPI_BB = 3 };
 constexpr int kBuilderWarps = 4;                // A_IM2COL only: 128 threads assemble the A tiles in shared memory
 constexpr int kThreadsBuilder = kThreads + 32 * kBuilderWarps;   // 448
 constexpr int kMaxHalo = 8;                     // A_IM2COL: halo ring depth (TMA latency of the small-row boxes is ~3 us)
-constexpr int kPayloadBytes = 220 * 1024;       // operand stages (+ halo buffers); barriers live right behind
+constexpr int kStgPitch = 80;                   // bytes per staged row: 32 bf16 + 16 pad (conflict-free 16-byte accesses)
+constexpr int kStagingBytes = kEpiWarps * 32 * kStgPitch;   // 20 KiB: per-warp transpose buffers of the epilogue
+constexpr int kOperandBytes = 200 * 1024;       // operand stages (+ halo buffers)
+constexpr int kPayloadBytes = kOperandBytes + kStagingBytes;   // barriers live right behind       // operand stages (+ halo buffers); barriers live right behind
 constexpr int kSmemBytes = kPayloadBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 
 enum { A_FLAT = 0, A_TILE4D = 1, A_IM2COL = 2 };
@@ -83,6 +86,33 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == 1) return fmaxf(v, 0.f);
     if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
     return v;
+}
+
+// Coalesced bf16 store of one 32-row x 32-column chunk held row-per-lane (pk = this lane's 32 values packed).
+// A row-per-lane STG.128 touches 32 different cache lines with 16 useful bytes each (measured: ~15k cycles per
+// 128x256 tile, the whole kernel waits on the store path).  Transposing through a per-warp shared-memory buffer
+// lets every store instruction write 8 rows x 64 contiguous bytes (full 32-byte sectors).
+__device__ __forceinline__ void store_chunk_bf16(uint32_t stg, int lane, const uint32_t (&pk)[16], bool valid, long long orow,
+                                                 __nv_bfloat16 *out, long long ldo, int col_base, int ncols_left) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * kStgPitch + i * 16), "r"(pk[4 * i]),
+                     "r"(pk[4 * i + 1]), "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                     : "memory");
+    __syncwarp();
+    const int part = lane & 3;
+    const uint32_t lo = (uint32_t)(orow & 0xffffffffLL), hi = (uint32_t)(orow >> 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rr = i * 8 + (lane >> 2);
+        const long long o = ((long long)__shfl_sync(0xffffffffu, hi, rr) << 32) | (long long)__shfl_sync(0xffffffffu, lo, rr);
+        const bool ok = __shfl_sync(0xffffffffu, valid ? 1 : 0, rr) != 0;
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(stg + rr * kStgPitch + part * 16));
+        if (ok && part * 8 < ncols_left) *reinterpret_cast<uint4 *>(out + o * ldo + col_base + part * 8) = v;
+    }
+    __syncwarp();
 }
 
 #define EWVIT_TRACE(role, tile, k)                                                                  \
@@ -342,6 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int r = q * 32 + lane;            // row of the tile owned by this thread
         const int gtid = (threadIdx.x - 64) & 127;
         float *g_scale = s_scale + grp * kBN, *g_shift = s_shift + grp * kBN;
+        const uint32_t stg = smem_base + kOperandBytes + (uint32_t)(warp - 2) * (32 * kStgPitch);
         const int acc = grp;
         uint32_t acc_phase = 0;
         int cur_nt = -1;
@@ -401,14 +432,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ewvit::tmem_ld_32x32(t_row + c * 32, v);
                 ewvit::tmem_ld_wait();
                 const int col0 = n_t * kBN + c * 32;
-                if (!valid) continue;
                 if (kEpi == EPI_BB) {
-                    // bias (+ SiLU / ReLU) (+ bf16 residual) -> bf16, 8 columns (16 bytes) at a time, masked past N
-                    __nv_bfloat16 *orow_p = static_cast<__nv_bfloat16 *>(p.out) + orow * p.ldo + p.col_off;
+                    // bias (+ SiLU / ReLU) (+ bf16 residual) -> bf16; columns past N are computed but never stored
+                    uint32_t pk[16];
 #pragma unroll
                     for (int g8 = 0; g8 < 4; ++g8) {
                         const int col = col0 + g8 * 8;
-                        if (col >= p.N) break;
                         float f8[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) f8[i] = __uint_as_float(v[g8 * 8 + i]) + g_shift[c * 32 + g8 * 8 + i];
@@ -419,7 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int i = 0; i < 8; ++i) f8[i] = fmaxf(f8[i], 0.f);
                         }
-                        if (p.residual_bf16) {   // skip connection is added AFTER the activation (FusedMBConv/MBConv)
+                        if (p.residual_bf16 && valid && col < p.N) {   // skip connection is added AFTER the activation
                             const uint4 rv = *reinterpret_cast<const uint4 *>(p.residual_bf16 + orow * p.ldr + col);
                             const __nv_bfloat162 *rp = reinterpret_cast<const __nv_bfloat162 *>(&rv);
 #pragma unroll
@@ -429,17 +458,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 f8[2 * i + 1] += r2.y;
                             }
                         }
-                        uint4 pk;
-                        __nv_bfloat162 b0 = __floats2bfloat162_rn(f8[0], f8[1]), b1 = __floats2bfloat162_rn(f8[2], f8[3]);
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(f8[4], f8[5]), b3 = __floats2bfloat162_rn(f8[6], f8[7]);
-                        pk.x = *reinterpret_cast<uint32_t *>(&b0);
-                        pk.y = *reinterpret_cast<uint32_t *>(&b1);
-                        pk.z = *reinterpret_cast<uint32_t *>(&b2);
-                        pk.w = *reinterpret_cast<uint32_t *>(&b3);
-                        *reinterpret_cast<uint4 *>(orow_p + col) = pk;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const __nv_bfloat162 bb = __floats2bfloat162_rn(f8[2 * i], f8[2 * i + 1]);
+                            pk[g8 * 4 + i] = *reinterpret_cast<const uint32_t *>(&bb);
+                        }
                     }
+                    store_chunk_bf16(stg, lane, pk, valid, orow, static_cast<__nv_bfloat16 *>(p.out), p.ldo, p.col_off + col0,
+                                     p.N - col0);
                     continue;
                 }
+                if (kEpi != EPI_CONV && !valid) continue;
                 if (kEpi == EPI_PARTIAL) {
                     float4 *dst = reinterpret_cast<float4 *>(p.partial + ((long long)sp * p.M + orow) * p.N + col0);
 #pragma unroll
@@ -482,6 +511,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.out) + orow * p.ldo + p.col_off + col0);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                } else if (kEpi == EPI_CONV) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const __nv_bfloat162 bb = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                        pk[i] = *reinterpret_cast<const uint32_t *>(&bb);
+                    }
+                    store_chunk_bf16(stg, lane, pk, valid, orow, static_cast<__nv_bfloat16 *>(p.out), p.ldo, p.col_off + col0, 32);
                 } else {
                     uint4 *dst = reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(p.out) + orow * p.ldo + p.col_off + col0);
 #pragma unroll
@@ -559,7 +596,7 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams p, 
         EWVIT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kBuilder, kBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    if (p.stages <= 0) p.stages = kBN == 128 ? kStages : kPayloadBytes / (kTileBytes + kBN * BK * 2);
+    if (p.stages <= 0) p.stages = kBN == 128 ? kStages : kOperandBytes / (kTileBytes + kBN * BK * 2);
     p.trace = g_trace;
     long long work = (long long)p.tiles_m * p.tiles_n * p.splits;
     long long grid = ewvit_num_sms();
@@ -776,7 +813,8 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
     const int ho = (h - 1) / stride + 1, wo = (wd - 1) / stride + 1;
     GemmParams p = {};
     // column tile: 256 wide when cout > 128, so A is fetched (or assembled) once per 256 output channels
-    const int bn = cout > 128 ? 256 : 128;
+    // (the stride-2 halo of the assembled path is 4x larger: keep 128-wide tiles there so two halo buffers still fit)
+    const int bn = (cout > 128 && !(ksize == 3 && cin < BK && stride == 2)) ? 256 : 128;
     const int stage_bytes = kTileBytes + bn * BK * 2;
     p.N = cout;
     p.tiles_n = (cout + bn - 1) / bn;
@@ -839,8 +877,8 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
             p.halo_bytes = p.halo_nb * plane_payload;                   // bytes the TMA unit reports on the mbarrier
             p.halo_stride = (p.halo_nb * p.plane_bytes + 1023) & ~1023;
             p.stages = bn == 256 ? 3 : 4;
-            if ((kPayloadBytes - p.stages * stage_bytes) / p.halo_stride < 2) p.stages -= 1;
-            p.halo_bufs = (kPayloadBytes - p.stages * stage_bytes) / p.halo_stride;
+            while (p.stages > 2 && (kOperandBytes - p.stages * stage_bytes) / p.halo_stride < 2) p.stages -= 1;
+            p.halo_bufs = (kOperandBytes - p.stages * stage_bytes) / p.halo_stride;
             if (p.halo_bufs > kMaxHalo) p.halo_bufs = kMaxHalo;
             EWVIT_REQUIRE(p.halo_bufs >= 2, EWVIT_ERR_UNSUPPORTED, "ewvit_conv_nhwc_bf16: halo too large");
             p.chunks_per_tap = 1;
