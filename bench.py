@@ -190,15 +190,36 @@ def main():
             dist.all_gather(gathered, out["logits"])
         return out["logits"]
 
-    x_stage = torch.empty_like(x_dev)
+    # e2e: pinned host frames -> device -> forward -> logits back to the host, every step.  Two device staging
+    # buffers and a copy stream let the H2D copy of step i+1 run under the compute of step i (each step still
+    # copies its own 308 MB of input and reads its own result back inside the timed region).
+    x_stage = [torch.empty_like(x_dev) for _ in range(2)]
     logits_host = torch.empty(VIDEOS, 1).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {"i": 0, "primed": False}
+
+    def issue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])               # the forward that last read this buffer is done
+            x_stage[slot].copy_(x_host, non_blocking=True)       # H2D of one step's frames (pinned)
+            copied[slot].record(copy_stream)
 
     def step_e2e():
-        x_stage.copy_(x_host, non_blocking=True)                 # H2D of this step's frames (pinned)
-        out = model(x_stage, BATCH_SIZE, "dynamic")
+        i = e2e_state["i"]
+        slot = i & 1
+        if not e2e_state["primed"]:
+            issue_copy(slot)
+            e2e_state["primed"] = True
+        issue_copy(slot ^ 1)                                     # next step's input streams in under this step's compute
+        torch.cuda.current_stream().wait_event(copied[slot])
+        out = model(x_stage[slot], BATCH_SIZE, "dynamic")
+        consumed[slot].record()
         if world > 1:
             dist.all_gather(gathered, out["logits"])
         logits_host.copy_(out["logits"], non_blocking=True)      # D2H of the step's result
+        e2e_state["i"] = i + 1
         return logits_host
 
     def barrier():
