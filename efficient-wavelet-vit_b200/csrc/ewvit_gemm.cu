@@ -78,6 +78,7 @@ struct GemmParams {
     int halo_bufs;       // halo ring depth (<= kMaxHalo)
     int halo_nb;         // the halo is fetched as halo_nb boxes of halo_ppb pixels x halo_h rows ("planes"): rows of
     int halo_ppb;        // halo_ppb*cin contiguous elements keep the TMA row count ~10x lower than per-pixel rows
+    int dbg;             // debug experiments (ewvit_debug_set_flags): 1 = skip epilogue stores, 2 = skip activation, 4 = skip staging transpose
     long long *trace;    // debug: clock64 stamps of CTA 0, [4 roles][64 tiles][4] (ewvit_debug_set_trace)
     int plane_bytes;     // distance between planes in shared memory (128-byte aligned, >= halo_h*halo_ppb*cin*2)
 };
@@ -441,7 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float f8[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) f8[i] = __uint_as_float(v[g8 * 8 + i]) + g_shift[c * 32 + g8 * 8 + i];
-                        if (p.act == 3) {
+                        if (p.act == 3 && !(p.dbg & 2)) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) f8[i] = ewvit::silu_fast(f8[i]);
                         } else if (p.act == 1) {
@@ -464,8 +465,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             pk[g8 * 4 + i] = *reinterpret_cast<const uint32_t *>(&bb);
                         }
                     }
-                    store_chunk_bf16(stg, lane, pk, valid, orow, static_cast<__nv_bfloat16 *>(p.out), p.ldo, p.col_off + col0,
-                                     p.N - col0);
+                    if (!(p.dbg & 1))
+                        store_chunk_bf16(stg, lane, pk, valid, orow, static_cast<__nv_bfloat16 *>(p.out), p.ldo, p.col_off + col0,
+                                         p.N - col0);
+                    else if (pk[0] == 0x12345678u) static_cast<uint32_t *>(p.out)[0] = pk[1];   // keep the math alive
                     continue;
                 }
                 if (kEpi != EPI_CONV && !valid) continue;
@@ -586,6 +589,7 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ partial, int spli
 }
 
 static long long *g_trace = nullptr;
+static int g_dbg = 0;
 
 template <int kEpi, bool kBuilder, int kBN>
 int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams p, cudaStream_t stream) {
@@ -598,6 +602,7 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams p, 
     }
     if (p.stages <= 0) p.stages = kBN == 128 ? kStages : kOperandBytes / (kTileBytes + kBN * BK * 2);
     p.trace = g_trace;
+    p.dbg = g_dbg;
     long long work = (long long)p.tiles_m * p.tiles_n * p.splits;
     long long grid = ewvit_num_sms();
     if (grid > work) grid = work;
@@ -907,6 +912,11 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
 
 // Debug aid: when non-NULL, CTA 0 of every subsequent GEMM/conv launch writes clock64 stamps of its warp roles
 // to this device buffer ([4 roles][64 tiles][4] int64).  Not part of the hot path; pass NULL to switch it off.
+extern "C" int ewvit_debug_set_flags(int flags) {
+    g_dbg = flags;
+    return EWVIT_OK;
+}
+
 extern "C" int ewvit_debug_set_trace(void *device_buffer) {
     g_trace = static_cast<long long *>(device_buffer);
     return EWVIT_OK;

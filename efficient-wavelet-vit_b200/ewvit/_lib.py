@@ -43,6 +43,7 @@ SIGNATURES = {
     "ewvit_dwconv3x3_nhwc_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "ewvit_se_apply_nhwc_bf16": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     "ewvit_debug_set_trace": (c_int, [P]),
+    "ewvit_debug_set_flags": (c_int, [c_int]),
     "ewvit_video_head_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P, P, P, P, P, c_int, P, P]),
 }
 

@@ -468,6 +468,8 @@ class DamaRunner:
         self.wpack = pack_dama_weights(sd, dim, depth)
         self._pos_cache = {}
         self.side_stream = None
+        import os
+        self.overlap = os.environ.get("EWVIT_OVERLAP", "0") == "1"   # measured: no gain (every GEMM CTA fills an SM)
 
     def pos_index(self, b, k, batch_size, device):
         key = (b, k, batch_size, str(device))
@@ -481,8 +483,20 @@ class DamaRunner:
 
     def process_frames(self, frames, pos_index):
         """frames [n,3,H,W] -> (fused, space, freq) each [n, dim] fp32 (``_process_frame``, dama.py:130-169)."""
-        space = self.sfe.forward(frames, pos_index)
-        freq = self.mwt.forward(frames)
+        if self.overlap and TIMER is None:
+            # the two branches are independent until the fusion tail: run the frequency branch on a side stream so
+            # its kernels fill the tails / launch gaps of the ~170 short backbone kernels (and vice versa)
+            if self.side_stream is None:
+                self.side_stream = torch.cuda.Stream(device=frames.device)
+            main = torch.cuda.current_stream()
+            self.side_stream.wait_stream(main)
+            with torch.cuda.stream(self.side_stream):
+                freq = self.mwt.forward(frames)
+            space = self.sfe.forward(frames, pos_index)
+            main.wait_stream(self.side_stream)
+        else:
+            space = self.sfe.forward(frames, pos_index)
+            freq = self.mwt.forward(frames)
         with stage("dama.tail"):
             return ops.dama_tail(space, freq, self.wpack, self.heads, self.depth, LN_EPS)
 

@@ -233,6 +233,10 @@ EWVIT_API int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const float
  * clock64 stamps of its warp roles to this device buffer ([4 roles][64 tiles][4] int64).  NULL switches it off. */
 EWVIT_API int ewvit_debug_set_trace(void *device_buffer);
 
+/* Debug experiments on the tensor-core kernel's epilogue (bit 0: skip the global stores, bit 1: skip the
+ * activation).  0 restores normal behaviour.  Never set in production. */
+EWVIT_API int ewvit_debug_set_flags(int flags);
+
 #ifdef __cplusplus
 }
 #endif

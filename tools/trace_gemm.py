@@ -26,7 +26,7 @@ def run(name, fn):
     t = buf.cpu().view(4, 64, 4)
     t0 = int(t[t > 0].min())
     print(f"=== {name}")
-    for tile in range(8, 16):
+    for tile in range(8, 13):
         row = []
         for role, nm in enumerate(("tma", "mma", "epi0", "epi1")):
             v = t[role, tile]
@@ -36,7 +36,7 @@ def run(name, fn):
         print(f"tile {tile:2d}  " + "  ".join(row))
 
 
-x = torch.randn(n, 112, 112, 24, device="cuda").bfloat16()
+x = torch.randn(256, 112, 112, 24, device="cuda").bfloat16()
 w = engine._w3x3_tapmajor_padded(torch.randn(24, 24, 3, 3) * 0.07).cuda()
 b = torch.zeros(24, device="cuda")
 run("conv3 24->24 @112 (im2col, 4 kb/tile)", lambda: ops.conv_nhwc_bf16(x, w, 3, 1, bias=b, act="silu", residual=x))
@@ -55,3 +55,13 @@ w3 = (torch.randn(160, 960, device="cuda") * 0.03).bfloat16()
 b3 = torch.zeros(160, device="cuda")
 r3 = torch.randn(512, 14, 14, 160, device="cuda").bfloat16()
 run("conv1 960->160 @14 project + residual (15 kb/tile)", lambda: ops.conv_nhwc_bf16(x3, w3, 1, 1, bias=b3, act=None, residual=r3))
+
+x4 = torch.randn(256, 56, 56, 48, device="cuda").bfloat16()
+w4 = engine._w3x3_tapmajor_padded(torch.randn(192, 48, 3, 3) * 0.05).cuda()
+b4 = torch.zeros(192, device="cuda")
+run("conv3 48->192 @56 (im2col, 7 kb/tile, bn 256)", lambda: ops.conv_nhwc_bf16(x4, w4, 3, 1, bias=b4, act="silu"))
+x5 = torch.randn(256, 56, 56, 192, device="cuda").bfloat16()
+w5 = (torch.randn(48, 192, device="cuda") * 0.07).bfloat16()
+b5 = torch.zeros(48, device="cuda")
+r5 = torch.randn(256, 56, 56, 48, device="cuda").bfloat16()
+run("conv1 192->48 @56 project + residual (3 kb/tile)", lambda: ops.conv_nhwc_bf16(x5, w5, 1, 1, bias=b5, act=None, residual=r5))
