@@ -34,8 +34,8 @@ enum { EPI_CONV = 0, EPI_LINEAR = 1, EPI_PARTIAL = 2, EPI_BB = 3 };
 constexpr int kBuilderWarps = 4;                // A_IM2COL only: 128 threads assemble the A tiles in shared memory
 constexpr int kThreadsBuilder = kThreads + 32 * kBuilderWarps;   // 448
 constexpr int kMaxHalo = 8;                     // A_IM2COL: halo ring depth (TMA latency of the small-row boxes is ~3 us)
-constexpr int kStgPitch = 80;                   // bytes per staged row: 32 bf16 + 16 pad (conflict-free 16-byte accesses)
-constexpr int kStagingBytes = kEpiWarps * 32 * kStgPitch;   // 20 KiB: per-warp transpose buffers of the epilogue
+constexpr int kStgBytes = 32 * 64;               // one epilogue chunk: 32 rows x 32 bf16, dense, 64B-swizzled (TMA store box)
+constexpr int kStagingBytes = kEpiWarps * kStgBytes;   // 16 KiB: per-warp staging buffers of the epilogue
 constexpr int kOperandBytes = 200 * 1024;       // operand stages (+ halo buffers)
 constexpr int kPayloadBytes = kOperandBytes + kStagingBytes;   // barriers live right behind       // operand stages (+ halo buffers); barriers live right behind
 constexpr int kSmemBytes = kPayloadBytes + 1024 /*align slack*/ + 512 /*barriers*/;
@@ -89,31 +89,33 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
-// Coalesced bf16 store of one 32-row x 32-column chunk held row-per-lane (pk = this lane's 32 values packed).
-// A row-per-lane STG.128 touches 32 different cache lines with 16 useful bytes each (measured: ~15k cycles per
-// 128x256 tile, the whole kernel waits on the store path).  Transposing through a per-warp shared-memory buffer
-// lets every store instruction write 8 rows x 64 contiguous bytes (full 32-byte sectors).
-__device__ __forceinline__ void store_chunk_bf16(uint32_t stg, int lane, const uint32_t (&pk)[16], bool valid, long long orow,
-                                                 __nv_bfloat16 *out, long long ldo, int col_base, int ncols_left) {
+// bf16 store of one 32-row x 32-column chunk held row-per-lane (pk = this lane's 32 values packed) through the TMA
+// unit: the warp writes the chunk into its shared-memory staging buffer (dense 64-byte rows, 64B-swizzled so the
+// 16-byte writes are conflict-free) and one lane issues a bulk tensor store.  The LSU never sees the scattered
+// row-per-lane pattern (32 cache lines x 16 bytes per STG measured ~15k cycles per 128x256 tile), stores drain
+// asynchronously while the warp computes the next chunk, and rows/columns outside the tensor are clipped by TMA.
+__device__ __forceinline__ void stage_chunk_bf16(uint32_t stg, int lane, const uint32_t (&pk)[16]) {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has finished reading the buffer
+    __syncwarp();
+    const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * kStgPitch + i * 16), "r"(pk[4 * i]),
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + (((uint32_t)i ^ sw) << 4)), "r"(pk[4 * i]),
                      "r"(pk[4 * i + 1]), "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
                      : "memory");
+    ewvit::fence_proxy_async();
     __syncwarp();
-    const int part = lane & 3;
-    const uint32_t lo = (uint32_t)(orow & 0xffffffffLL), hi = (uint32_t)(orow >> 32);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int rr = i * 8 + (lane >> 2);
-        const long long o = ((long long)__shfl_sync(0xffffffffu, hi, rr) << 32) | (long long)__shfl_sync(0xffffffffu, lo, rr);
-        const bool ok = __shfl_sync(0xffffffffu, valid ? 1 : 0, rr) != 0;
-        uint4 v;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                     : "r"(stg + rr * kStgPitch + part * 16));
-        if (ok && part * 8 < ncols_left) *reinterpret_cast<uint4 *>(out + o * ldo + col_base + part * 8) = v;
-    }
-    __syncwarp();
+}
+__device__ __forceinline__ void tma_store_2d(const void *tmap, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void *tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap), "r"(src),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
 #define EWVIT_TRACE(role, tile, k)                                                                  \
@@ -123,7 +125,8 @@ __device__ __forceinline__ void store_chunk_bf16(uint32_t stg, int lane, const u
 
 template <int kEpi, bool kBuilder, int kBN>
 __global__ void __launch_bounds__(kBuilder ? kThreadsBuilder : kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + kPayloadBytes);
@@ -373,7 +376,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int r = q * 32 + lane;            // row of the tile owned by this thread
         const int gtid = (threadIdx.x - 64) & 127;
         float *g_scale = s_scale + grp * kBN, *g_shift = s_shift + grp * kBN;
-        const uint32_t stg = smem_base + kOperandBytes + (uint32_t)(warp - 2) * (32 * kStgPitch);
+        const uint32_t stg = smem_base + kOperandBytes + (uint32_t)(warp - 2) * kStgBytes;
         const int acc = grp;
         uint32_t acc_phase = 0;
         int cur_nt = -1;
@@ -399,6 +402,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
             bool valid, zero = false;
             long long orow;
+            int st_x = 0, st_y = 0, st_img = 0;     // TMA-store box origin of this warp's 32 rows (2 pixel rows x 16 pixels)
             if (p.a_mode == A_FLAT) {
                 orow = (long long)m_t * BM + r;
                 valid = orow < p.M;
@@ -415,6 +419,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int oy = ty * p.box_h + r / p.box_w, ox = tx * p.box_w + r % p.box_w;
                 valid = (oy < p.out_h) && (ox < p.out_w);
                 orow = (long long)img * p.out_img_rows + (long long)(oy + p.out_pad) * p.out_wp + ox + p.out_pad;
+                st_x = tx * p.box_w + p.out_pad;
+                st_y = ty * p.box_h + (q * 32) / p.box_w + p.out_pad;
+                st_img = img;
             }
             if (kEpi == EPI_BB && p.residual_bf16 && valid) {   // start pulling the skip-connection row while the MMAs run
                 const __nv_bfloat16 *rp = p.residual_bf16 + orow * p.ldr + n_t * kBN;
@@ -465,10 +472,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             pk[g8 * 4 + i] = *reinterpret_cast<const uint32_t *>(&bb);
                         }
                     }
-                    if (!(p.dbg & 1))
-                        store_chunk_bf16(stg, lane, pk, valid, orow, static_cast<__nv_bfloat16 *>(p.out), p.ldo, p.col_off + col0,
-                                         p.N - col0);
-                    else if (pk[0] == 0x12345678u) static_cast<uint32_t *>(p.out)[0] = pk[1];   // keep the math alive
+                    if (!(p.dbg & 1)) {
+                        stage_chunk_bf16(stg, lane, pk);
+                        if (lane == 0) {
+                            if (p.a_mode == A_FLAT) tma_store_2d(&tmC, stg, p.col_off + col0, m_t * BM + q * 32);
+                            else tma_store_4d(&tmC, stg, p.col_off + col0, st_x, st_y, st_img);
+                        }
+                    } else if (pk[0] == 0x12345678u) static_cast<uint32_t *>(p.out)[0] = pk[1];   // keep the math alive
                     continue;
                 }
                 if (kEpi != EPI_CONV && !valid) continue;
@@ -521,7 +531,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const __nv_bfloat162 bb = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
                         pk[i] = *reinterpret_cast<const uint32_t *>(&bb);
                     }
-                    store_chunk_bf16(stg, lane, pk, valid, orow, static_cast<__nv_bfloat16 *>(p.out), p.ldo, p.col_off + col0, 32);
+                    stage_chunk_bf16(stg, lane, pk);
+                    if (lane == 0) {
+                        if (p.a_mode == A_FLAT) tma_store_2d(&tmC, stg, p.col_off + col0, m_t * BM + q * 32);
+                        else tma_store_4d(&tmC, stg, p.col_off + col0, st_x, st_y, st_img);
+                    }
                 } else {
                     uint4 *dst = reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(p.out) + orow * p.ldo + p.col_off + col0);
 #pragma unroll
@@ -546,6 +560,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (q == 2 && lane == 0) EWVIT_TRACE(2 + grp, it, 3);
             acc_phase ^= 1;
         }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging buffers are read out before the CTA retires
     }
 
     ewvit::tc_fence_before();
@@ -592,7 +607,7 @@ static long long *g_trace = nullptr;
 static int g_dbg = 0;
 
 template <int kEpi, bool kBuilder, int kBN>
-int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams p, cudaStream_t stream) {
+int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, GemmParams p, cudaStream_t stream) {
     static bool attr_set[64] = {false};
     int dev = 0;
     EWVIT_CUDA_OK(cudaGetDevice(&dev));
@@ -607,20 +622,21 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams p, 
     long long grid = ewvit_num_sms();
     if (grid > work) grid = work;
     if (grid <= 0) return EWVIT_OK;
-    gemm_tc_kernel<kEpi, kBuilder, kBN><<<(unsigned)grid, kBuilder ? kThreadsBuilder : kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+    gemm_tc_kernel<kEpi, kBuilder, kBN><<<(unsigned)grid, kBuilder ? kThreadsBuilder : kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, p);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }
 
-int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int epi, cudaStream_t stream, int bn = BN) {
-    if (epi == EPI_CONV) return launch_gemm_t<EPI_CONV, false, 128>(tmA, tmB, p, stream);
+int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p, int epi, cudaStream_t stream,
+                int bn = BN) {
+    if (epi == EPI_CONV) return launch_gemm_t<EPI_CONV, false, 128>(tmA, tmB, tmC, p, stream);
     if (epi == EPI_BB) {
         if (p.a_mode == A_IM2COL)
-            return bn == 256 ? launch_gemm_t<EPI_BB, true, 256>(tmA, tmB, p, stream) : launch_gemm_t<EPI_BB, true, 128>(tmA, tmB, p, stream);
-        return bn == 256 ? launch_gemm_t<EPI_BB, false, 256>(tmA, tmB, p, stream) : launch_gemm_t<EPI_BB, false, 128>(tmA, tmB, p, stream);
+            return bn == 256 ? launch_gemm_t<EPI_BB, true, 256>(tmA, tmB, tmC, p, stream) : launch_gemm_t<EPI_BB, true, 128>(tmA, tmB, tmC, p, stream);
+        return bn == 256 ? launch_gemm_t<EPI_BB, false, 256>(tmA, tmB, tmC, p, stream) : launch_gemm_t<EPI_BB, false, 128>(tmA, tmB, tmC, p, stream);
     }
-    if (epi == EPI_PARTIAL) return launch_gemm_t<EPI_PARTIAL, false, 128>(tmA, tmB, p, stream);
-    return launch_gemm_t<EPI_LINEAR, false, 128>(tmA, tmB, p, stream);
+    if (epi == EPI_PARTIAL) return launch_gemm_t<EPI_PARTIAL, false, 128>(tmA, tmB, tmC, p, stream);
+    return launch_gemm_t<EPI_LINEAR, false, 128>(tmA, tmB, tmC, p, stream);
 }
 
 }  // namespace
@@ -656,6 +672,34 @@ int ewvit_make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uin
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     EWVIT_REQUIRE(r == CUDA_SUCCESS, EWVIT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+    return EWVIT_OK;
+}
+
+// Output tensor map of the TMA-store epilogues: bf16, 64-byte swizzle, box = 32 channels x 32 rows (flat) or
+// 32 channels x 16 pixels x 2 pixel rows (tiled NHWC, optionally with a one-pixel border).
+static int make_out_tmap(CUtensorMap *out, void *base, bool flat, long long rows, int ldc, int n, int h_total, int w_total,
+                         int h_extent = 0, int w_extent = 0) {
+    ewvit_encode_tiled_fn enc = ewvit_get_encode_tiled();
+    EWVIT_REQUIRE(enc != nullptr, EWVIT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[4], gstr[3];
+    cuuint32_t bdim[4], es[4] = {1, 1, 1, 1};
+    int rank;
+    if (flat) {
+        rank = 2;
+        gdim[0] = (cuuint64_t)ldc; gdim[1] = (cuuint64_t)rows;
+        gstr[0] = (cuuint64_t)ldc * 2;
+        bdim[0] = 32; bdim[1] = 32;
+    } else {
+        rank = 4;
+        // the extents may stop short of the pitch (a trailing border column/row that must never be written)
+        gdim[0] = (cuuint64_t)ldc; gdim[1] = (cuuint64_t)(w_extent ? w_extent : w_total);
+        gdim[2] = (cuuint64_t)(h_extent ? h_extent : h_total); gdim[3] = (cuuint64_t)n;
+        gstr[0] = (cuuint64_t)ldc * 2; gstr[1] = (cuuint64_t)w_total * ldc * 2; gstr[2] = (cuuint64_t)h_total * w_total * ldc * 2;
+        bdim[0] = 32; bdim[1] = 16; bdim[2] = 2; bdim[3] = 1;
+    }
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gdim, gstr, bdim, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    EWVIT_REQUIRE(r == CUDA_SUCCESS, EWVIT_ERR_CUDA, "cuTensorMapEncodeTiled (output map) failed with CUresult %d", (int)r);
     return EWVIT_OK;
 }
 
@@ -704,7 +748,7 @@ extern "C" int ewvit_linear_bf16(const void *a, const void *w, int64_t M, int N,
     p.out = out; p.out_fp32 = out_fp32; p.ldo = ldo; p.col_off = 0;
     p.scale = scale; p.shift = shift; p.act = act; p.residual = residual; p.ldr = ldr;
     p.partial = p.splits > 1 ? workspace : nullptr;
-    rc = launch_gemm(tmA, tmB, p, p.splits > 1 ? EPI_PARTIAL : EPI_LINEAR, (cudaStream_t)stream);
+    rc = launch_gemm(tmA, tmB, tmA /*no TMA store in these epilogues*/, p, p.splits > 1 ? EPI_PARTIAL : EPI_LINEAR, (cudaStream_t)stream);
     if (rc != EWVIT_OK) return rc;
     if (p.splits > 1) {
         const long long total = M * (N / 4);
@@ -793,7 +837,13 @@ extern "C" int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, in
                 p.tap_a1[dy * 3 + dx] = dy + off;
             }
     }
-    return launch_gemm(tmA, tmB, p, EPI_CONV, (cudaStream_t)stream);
+    CUtensorMap tmC;
+    if (flat)
+        rc = make_out_tmap(&tmC, y, true, (long long)n * hin * win, y_ldc, 0, 0, 0);
+    else
+        rc = make_out_tmap(&tmC, y, false, 0, y_ldc, n, ho + 2 * p.out_pad, wo + 2 * p.out_pad, ho + p.out_pad, wo + p.out_pad);
+    if (rc != EWVIT_OK) return rc;
+    return launch_gemm(tmA, tmB, tmC, p, EPI_CONV, (cudaStream_t)stream);
 }
 
 
@@ -907,7 +957,13 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
                 }
         }
     }
-    return launch_gemm(tmA, tmB, p, EPI_BB, (cudaStream_t)stream, bn);
+    CUtensorMap tmC;
+    if (ksize == 1)
+        rc = make_out_tmap(&tmC, y, true, (long long)n * h * wd, cout, 0, 0, 0);
+    else
+        rc = make_out_tmap(&tmC, y, false, 0, cout, n, ho, wo);
+    if (rc != EWVIT_OK) return rc;
+    return launch_gemm(tmA, tmB, tmC, p, EPI_BB, (cudaStream_t)stream, bn);
 }
 
 // Debug aid: when non-NULL, CTA 0 of every subsequent GEMM/conv launch writes clock64 stamps of its warp roles
