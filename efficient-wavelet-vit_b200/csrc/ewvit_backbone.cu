@@ -69,27 +69,33 @@ template <int SC>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ x, const float *__restrict__ w,
                                                         const float *__restrict__ bias, __nv_bfloat16 *__restrict__ y,
                                                         float *__restrict__ pooled, int n, int h, int wd, int ho, int wo,
-                                                        int c, int stride, int fpc) {
+                                                        int c, int stride, int fpc, int fb) {
+    // fb = frames staged and processed together (small planes: 4 frames of 7x7 keep all pixel lanes busy and
+    // amortise the barriers); fpc = frames per CTA (multiple of fb)
     constexpr int G = SC / 8;            // 8-channel groups per slab
     constexpr int PL = 256 / G;          // pixel lanes
     extern __shared__ __align__(16) unsigned char dw_smem[];
-    const int plane = h * wd * SC;                                                      // elements per stage
-    __nv_bfloat16 *s_in = reinterpret_cast<__nv_bfloat16 *>(dw_smem);                  // [2][h*wd][SC]
-    float *s_w = reinterpret_cast<float *>(dw_smem + (size_t)2 * plane * 2);            // [9][SC] then bias [SC]
-    float *s_sum = s_w + 10 * SC;                                                       // [PL][SC + 1]
+    const int plane = h * wd * SC;                                                      // elements of one frame's slab
+    __nv_bfloat16 *s_in = reinterpret_cast<__nv_bfloat16 *>(dw_smem);                  // [2][fb][h*wd][SC]
+    float *s_w = reinterpret_cast<float *>(dw_smem + (size_t)2 * fb * plane * 2);       // [9][SC] then bias [SC]
+    float *s_sum = s_w + 10 * SC;                                                       // [fb][PL][SC + 1]
     const int slabs = c / SC;
     const int cs = (blockIdx.x % slabs) * SC;
     const int f0 = (blockIdx.x / slabs) * fpc;
     const int f1 = min(n, f0 + fpc);
     const int tid = threadIdx.x;
+    const int npix = ho * wo;
 
     auto stage_in = [&](int frame, int buf) {
-        const __nv_bfloat16 *px = x + (long long)frame * h * wd * c + cs;
-        __nv_bfloat16 *dstb = s_in + (size_t)buf * plane;
-        for (int i = tid; i < h * wd * G; i += 256) {
-            const int p = i / G, g = i - p * G;
-            const uint32_t dst = ewvit::smem_u32(dstb + p * SC + g * 8);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(px + (long long)p * c + g * 8) : "memory");
+        const int nf = min(fb, f1 - frame);
+        for (int fl = 0; fl < nf; ++fl) {
+            const __nv_bfloat16 *px = x + (long long)(frame + fl) * h * wd * c + cs;
+            __nv_bfloat16 *dstb = s_in + ((size_t)buf * fb + fl) * plane;
+            for (int i = tid; i < h * wd * G; i += 256) {
+                const int p = i / G, g = i - p * G;
+                const uint32_t dst = ewvit::smem_u32(dstb + p * SC + g * 8);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(px + (long long)p * c + g * 8) : "memory");
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -106,22 +112,29 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16 *__r
 #pragma unroll
     for (int j = 0; j < 8; ++j) br[j] = s_w[9 * SC + g * 8 + j];
 
-    for (int f = f0; f < f1; ++f) {
-        const int buf = (f - f0) & 1;
-        if (f + 1 < f1) {
-            stage_in(f + 1, buf ^ 1);
+    int buf = 0;
+    for (int f = f0; f < f1; f += fb, buf ^= 1) {
+        const int nf = min(fb, f1 - f);
+        if (f + fb < f1) {
+            stage_in(f + fb, buf ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const __nv_bfloat16 *sp = s_in + (size_t)buf * plane + g * 8;
-        __nv_bfloat16 *py = y + (long long)f * ho * wo * c + cs + g * 8;
         float sum[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) sum[j] = 0.f;
-        for (int o = pl; o < ho * wo; o += PL) {
+        int cur_fl = 0;
+        for (int item = pl; item < nf * npix; item += PL) {
+            const int fl = item / npix, o = item - fl * npix;
+            if (fl != cur_fl) {      // this thread's items moved on to the next frame: park the finished partial sum
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s_sum[(cur_fl * PL + pl) * (SC + 1) + g * 8 + j] = sum[j]; sum[j] = 0.f; }
+                cur_fl = fl;
+            }
             const int oy = o / wo, ox = o - oy * wo;
+            const __nv_bfloat16 *sp = s_in + ((size_t)buf * fb + fl) * plane + g * 8;
             float a[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[j] = br[j];
@@ -152,44 +165,80 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16 *__r
                 sum[2 * j] += r.x;
                 sum[2 * j + 1] += r.y;
             }
-            *reinterpret_cast<uint4 *>(py + (long long)o * c) = pk;
+            *reinterpret_cast<uint4 *>(y + ((long long)(f + fl) * npix + o) * c + cs + g * 8) = pk;
         }
         if (pooled) {
+            // every (frame, pixel lane) slot is written exactly once: by the flush above, here, or as an explicit zero
+            for (int fl = 0; fl < nf; ++fl) {
+                const bool mine = fl == cur_fl, later = fl > cur_fl;
+                if (mine || later) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s_sum[pl * (SC + 1) + g * 8 + j] = sum[j];
+                    for (int j = 0; j < 8; ++j) s_sum[(fl * PL + pl) * (SC + 1) + g * 8 + j] = mine ? sum[j] : 0.f;
+                }
+            }
             __syncthreads();
-            if (tid < SC) {
-                float s = 0.f;
-                for (int i = 0; i < PL; ++i) s += s_sum[i * (SC + 1) + tid];
-                pooled[(long long)f * c + cs + tid] = s / (float)(ho * wo);
+            for (int i = tid; i < nf * SC; i += 256) {
+                const int fl = i / SC, ch = i - fl * SC;
+                float t = 0.f;
+                for (int k = 0; k < PL; ++k) t += s_sum[(fl * PL + k) * (SC + 1) + ch];
+                pooled[(long long)(f + fl) * c + cs + ch] = t / (float)npix;
             }
         }
         __syncthreads();   // everyone is done with this stage buffer (and s_sum) before it is refilled
     }
 }
 
-// ---- squeeze-excitation gate: gate[n, c] = sigmoid(W2 * silu(W1 * pooled[n] + b1) + b2); one CTA per frame
+// ---- squeeze-excitation gate: gate[n, c] = sigmoid(W2 * silu(W1 * pooled[n] + b1) + b2).
+//      One CTA serves kSeF frames so every weight row is read from L2 once per kSeF frames (the two FC matrices are
+//      ~0.8 MB at c = 1536: one-frame CTAs made the 512-frame launch read 400 MB of weights).
+constexpr int kSeF = 1;
 __global__ void __launch_bounds__(256) se_gate_kernel(const float *__restrict__ pooled, const float *__restrict__ w1,
                                                       const float *__restrict__ b1, const float *__restrict__ w2t,
-                                                      const float *__restrict__ b2, float *__restrict__ gate, int c, int sq) {
+                                                      const float *__restrict__ b2, float *__restrict__ gate, int n, int c, int sq) {
     extern __shared__ float se_sm[];
-    float *s_pool = se_sm, *s_hid = se_sm + c;
-    const long long img = blockIdx.x;
+    float *s_pool = se_sm;                 // [kSeF][c]
+    float *s_hid = se_sm + kSeF * c;       // [kSeF][sq]
+    const int f0 = blockIdx.x * kSeF;
+    const int nf = min(kSeF, n - f0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < c; i += 256) s_pool[i] = pooled[img * c + i];
+    for (int i = tid; i < kSeF * c; i += 256) {
+        const int f = i / c;
+        s_pool[i] = f < nf ? pooled[(long long)(f0 + f) * c + (i - f * c)] : 0.f;
+    }
     __syncthreads();
     for (int j = warp; j < sq; j += 8) {
-        float s = 0.f;
-        for (int k = lane; k < c; k += 32) s = fmaf(w1[(long long)j * c + k], s_pool[k], s);
+        float acc[kSeF];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) s_hid[j] = silu(s + b1[j]);
+        for (int f = 0; f < kSeF; ++f) acc[f] = 0.f;
+#pragma unroll 4
+        for (int k = lane; k < c; k += 32) {
+            const float wv = w1[(long long)j * c + k];
+#pragma unroll
+            for (int f = 0; f < kSeF; ++f) acc[f] = fmaf(wv, s_pool[f * c + k], acc[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < kSeF; ++f) {
+            float v = acc[f];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_hid[f * sq + j] = silu(v + b1[j]);
+        }
     }
     __syncthreads();
     for (int i = tid; i < c; i += 256) {
-        float s = b2[i];
-        for (int j = 0; j < sq; ++j) s = fmaf(w2t[(long long)j * c + i], s_hid[j], s);
-        gate[img * c + i] = 1.f / (1.f + __expf(-s));
+        float acc[kSeF];
+        const float bb = b2[i];
+#pragma unroll
+        for (int f = 0; f < kSeF; ++f) acc[f] = bb;
+#pragma unroll 8
+        for (int j = 0; j < sq; ++j) {
+            const float wv = w2t[(long long)j * c + i];
+#pragma unroll
+            for (int f = 0; f < kSeF; ++f) acc[f] = fmaf(wv, s_hid[f * sq + j], acc[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < kSeF; ++f)
+            if (f < nf) gate[(long long)(f0 + f) * c + i] = 1.f / (1.f + __expf(-acc[f]));
     }
 }
 
@@ -246,7 +295,9 @@ extern "C" int ewvit_dwconv3x3_nhwc_bf16(const void *x, const float *w, const fl
     // 64-channel slabs when the staged input plane fits ~56 KB of shared memory, else 32-channel slabs
     const bool wide = (size_t)h * wd * 64 * 2 <= 50 * 1024;   // two stages of the slab's input plane
     const int sc = wide ? 64 : 32;
-    const size_t smem = (size_t)2 * h * wd * sc * 2 + (size_t)10 * sc * 4 + (size_t)(256 / (sc / 8)) * (sc + 1) * 4;
+    int fb = 1;                                                // frames processed together (small planes)
+    while (fb < 4 && (size_t)h * wd * sc * 2 * (fb * 2) <= 26 * 1024 && n % (fb * 2) == 0) fb *= 2;
+    const size_t smem = (size_t)2 * fb * h * wd * sc * 2 + (size_t)10 * sc * 4 + (size_t)fb * (256 / (sc / 8)) * (sc + 1) * 4;
     EWVIT_REQUIRE(smem <= 200 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_dwconv3x3_nhwc_bf16: %dx%d input plane too large for the staged kernel", h, wd);
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -258,14 +309,15 @@ extern "C" int ewvit_dwconv3x3_nhwc_bf16(const void *x, const float *w, const fl
     }
     // frames per CTA: amortise the weight prologue while keeping >= ~4 CTAs per SM in the grid
     int fpc = 8;
-    while (fpc > 1 && (long long)((n + fpc - 1) / fpc) * (c / sc) < 4LL * ewvit_num_sms()) fpc /= 2;
+    while (fpc > fb && (long long)((n + fpc - 1) / fpc) * (c / sc) < 4LL * ewvit_num_sms()) fpc /= 2;
+    if (fpc < fb) fpc = fb;
     const unsigned grid = (unsigned)((long long)((n + fpc - 1) / fpc) * (c / sc));
     if (wide)
         dwconv3x3_kernel<64><<<grid, 256, smem, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16 *>(x), w, bias,
-                                                                        static_cast<__nv_bfloat16 *>(y), pooled, n, h, wd, ho, wo, c, stride, fpc);
+                                                                        static_cast<__nv_bfloat16 *>(y), pooled, n, h, wd, ho, wo, c, stride, fpc, fb);
     else
         dwconv3x3_kernel<32><<<grid, 256, smem, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16 *>(x), w, bias,
-                                                                        static_cast<__nv_bfloat16 *>(y), pooled, n, h, wd, ho, wo, c, stride, fpc);
+                                                                        static_cast<__nv_bfloat16 *>(y), pooled, n, h, wd, ho, wo, c, stride, fpc, fb);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }
@@ -276,10 +328,18 @@ extern "C" int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const floa
     if (n == 0) return EWVIT_OK;
     EWVIT_REQUIRE(x && pooled && w1 && b1 && w2t && b2 && gate_ws && ewvit_aligned16(x) && ewvit_aligned16(gate_ws), EWVIT_ERR_INVALID_ARG,
                   "ewvit_se_apply_nhwc_bf16: NULL or misaligned pointer");
-    EWVIT_REQUIRE(c % 8 == 0 && (c + sq) * 4 <= 48 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_se_apply_nhwc_bf16: c=%d sq=%d not supported", c, sq);
+    const size_t gate_smem = (size_t)kSeF * (c + sq) * sizeof(float);
+    EWVIT_REQUIRE(c % 8 == 0 && gate_smem <= 160 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_se_apply_nhwc_bf16: c=%d sq=%d not supported", c, sq);
     int rc = ewvit_check_device();
     if (rc != EWVIT_OK) return rc;
-    se_gate_kernel<<<(unsigned)n, 256, (c + sq) * sizeof(float), (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, gate_ws, c, sq);
+    static bool se_attr[64] = {false};
+    int dev = 0;
+    EWVIT_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !se_attr[dev]) {
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        if (dev >= 0 && dev < 64) se_attr[dev] = true;
+    }
+    se_gate_kernel<<<(unsigned)((n + kSeF - 1) / kSeF), 256, gate_smem, (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, gate_ws, n, c, sq);
     EWVIT_LAUNCH_OK();
     const long long total8 = (long long)n * hw * (c / 8);
     long long blocks = (total8 + 255) / 256;
