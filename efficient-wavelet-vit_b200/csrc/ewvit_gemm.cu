@@ -76,6 +76,9 @@ struct GemmParams {
     int halo_bytes;      // bytes of one halo buffer (TMA transaction size)
     int halo_stride;     // 1024-aligned distance between consecutive halo buffers
     int halo_bufs;       // halo ring depth (<= kMaxHalo)
+    int stage_bytes;     // ring slot size: A tile (+ B tile unless the weights are resident)
+    int b_res;           // A_IM2COL: all k-blocks of B stay resident in shared memory (loaded once per CTA)
+    int bres_off;        // byte offset of the resident B region
     int halo_nb;         // the halo is fetched as halo_nb boxes of halo_ppb pixels x halo_h rows ("planes"): rows of
     int halo_ppb;        // halo_ppb*cin contiguous elements keep the TMA row count ~10x lower than per-pixel rows
     int dbg;             // debug experiments (ewvit_debug_set_flags): 1 = skip epilogue stores, 2 = skip activation, 4 = skip staging transpose
@@ -133,8 +136,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     unsigned long long *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages,
                        *tempty = bars + 2 * kStages + kAccStages;
     unsigned long long *hfull = bars + 2 * kStages + 2 * kAccStages, *hempty = hfull + kMaxHalo;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(hempty + kMaxHalo);
-    constexpr int kStageB = kTileBytes + kBN * BK * 2;   // A tile + B tile of this column width
+    unsigned long long *bres_bar = hempty + kMaxHalo;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bres_bar + 1);
+    constexpr int kBTileB = kBN * BK * 2;               // B tile of this column width
     constexpr uint32_t kTmemColsT = kAccStages * kBN;
     __shared__ __align__(16) float s_scale[2 * kBN], s_shift[2 * kBN];
     __shared__ int s_koff[kBuilder ? 9 * 8 : 1];
@@ -142,18 +146,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler, too
     const int lane = threadIdx.x & 31;
     const int nstages = p.stages;
+    const uint32_t kStageB = (uint32_t)p.stage_bytes;    // A tile + B tile (A only when B is resident)
 
     if (threadIdx.x == 0) {
         ewvit::tma_prefetch_desc(&tmA);
         ewvit::tma_prefetch_desc(&tmB);
         for (int s = 0; s < kStages; ++s) {
-            ewvit::mbar_init(ewvit::smem_u32(&full[s]), kBuilder ? 2 : 1);
+            ewvit::mbar_init(ewvit::smem_u32(&full[s]), (kBuilder && !p.b_res) ? 2 : 1);
             ewvit::mbar_init(ewvit::smem_u32(&empty[s]), 1);
         }
         for (int a = 0; a < kAccStages; ++a) {
             ewvit::mbar_init(ewvit::smem_u32(&tfull[a]), 1);
             ewvit::mbar_init(ewvit::smem_u32(&tempty[a]), kEpiWarps / 2);
         }
+        ewvit::mbar_init(ewvit::smem_u32(bres_bar), 1);
         for (int a = 0; a < kMaxHalo; ++a) {
             ewvit::mbar_init(ewvit::smem_u32(&hfull[a]), 1);
             ewvit::mbar_init(ewvit::smem_u32(&hempty[a]), kBuilderWarps);
@@ -181,6 +187,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0, hb = 0;
         uint32_t phase = 0, hphase = 0;
         int tt = 0;
+        if (kBuilder && p.b_res) {     // weights are tiny and identical for every tile: fetch all k-blocks once
+            if (ewvit::elect_one()) {
+                const uint32_t bb = ewvit::smem_u32(bres_bar);
+                ewvit::mbar_expect_tx(bb, (uint32_t)(p.num_kb * kBTileB));
+                for (int kb = 0; kb < p.num_kb; ++kb)
+                    ewvit::tma_load_2d(smem_base + p.bres_off + kb * kBTileB, &tmB, kb * BK, 0, bb);
+            }
+            __syncwarp();
+        }
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tt) {
             if (lane == 0) EWVIT_TRACE(0, tt, 0);
             const int m_t = w % p.tiles_m;            // m fastest: a CTA keeps its column tile (and its staged
@@ -209,12 +224,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 __syncwarp();
                 if (++hb == p.halo_bufs) { hb = 0; hphase ^= 1; }
-                for (int kb = kb0; kb < kb1; ++kb) {
+                for (int kb = kb0; kb < kb1 && !p.b_res; ++kb) {
                     ewvit::mbar_wait(ewvit::smem_u32(&empty[stage]), phase ^ 1);
                     const uint32_t bar = ewvit::smem_u32(&full[stage]);
                     const uint32_t b_dst = smem_base + stage * kStageB + kTileBytes;
                     if (ewvit::elect_one()) {
-                        ewvit::mbar_expect_tx(bar, kBN * BK * 2);
+                        ewvit::mbar_expect_tx(bar, kBTileB);
                         ewvit::tma_load_2d(b_dst, &tmB, kb * BK, n_t * kBN, bar);
                     }
                     __syncwarp();
@@ -250,6 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int acc = 0;
         uint32_t acc_phase = 0;
         int tt = 0;
+        if (kBuilder && p.b_res) ewvit::mbar_wait(ewvit::smem_u32(bres_bar), 0);
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tt) {
             if (lane == 0) EWVIT_TRACE(1, tt, 0);
             const int wn = w / p.tiles_m;
@@ -268,7 +284,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (kb == kb0 && lane == 0) EWVIT_TRACE(1, tt, 2);
                 ewvit::tc_fence_after();
                 const uint32_t a_addr = smem_base + stage * kStageB;
-                const uint64_t a_desc = ewvit::umma_desc_sw128(a_addr), b_desc = ewvit::umma_desc_sw128(a_addr + kTileBytes);
+                const uint64_t a_desc = ewvit::umma_desc_sw128(a_addr);
+                const uint64_t b_desc = ewvit::umma_desc_sw128((kBuilder && p.b_res) ? smem_base + p.bres_off + kb * kBTileB : a_addr + kTileBytes);
                 const uint32_t ebar = ewvit::smem_u32(&empty[stage]);
                 const uint32_t first = kb > kb0 ? 1u : 0u;
                 if (ewvit::elect_one()) {
@@ -615,6 +632,7 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
         EWVIT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kBuilder, kBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
+    if (p.stage_bytes <= 0) p.stage_bytes = kTileBytes + kBN * BK * 2;
     if (p.stages <= 0) p.stages = kBN == 128 ? kStages : kOperandBytes / (kTileBytes + kBN * BK * 2);
     p.trace = g_trace;
     p.dbg = g_dbg;
@@ -931,11 +949,19 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
             p.plane_bytes = (plane_payload + 127) & ~127;                // TMA destinations must be 128-byte aligned
             p.halo_bytes = p.halo_nb * plane_payload;                   // bytes the TMA unit reports on the mbarrier
             p.halo_stride = (p.halo_nb * p.plane_bytes + 1023) & ~1023;
+            p.b_res = (p.tiles_n == 1 && num_kb * bn * BK * 2 <= 64 * 1024) ? 1 : 0;
+            int sbytes = stage_bytes, reserve = 0;
+            if (p.b_res) {                      // ring slots hold A only; the weights get their own region
+                sbytes = kTileBytes;
+                reserve = num_kb * bn * BK * 2;
+            }
+            p.stage_bytes = sbytes;
             p.stages = bn == 256 ? 3 : 4;
-            while (p.stages > 2 && (kOperandBytes - p.stages * stage_bytes) / p.halo_stride < 2) p.stages -= 1;
-            p.halo_bufs = (kOperandBytes - p.stages * stage_bytes) / p.halo_stride;
+            while (p.stages > 2 && (kOperandBytes - reserve - p.stages * sbytes) / p.halo_stride < 2) p.stages -= 1;
+            p.halo_bufs = (kOperandBytes - reserve - p.stages * sbytes) / p.halo_stride;
             if (p.halo_bufs > kMaxHalo) p.halo_bufs = kMaxHalo;
             EWVIT_REQUIRE(p.halo_bufs >= 2, EWVIT_ERR_UNSUPPORTED, "ewvit_conv_nhwc_bf16: halo too large");
+            p.bres_off = p.stages * sbytes + p.halo_bufs * p.halo_stride;
             p.chunks_per_tap = 1;
             // activation viewed as [n][h][wd*cin]: a run of pixels of one image row is one contiguous TMA row
             uint64_t dims3[3] = {(uint64_t)wd * cin, (uint64_t)h, (uint64_t)n};
