@@ -31,8 +31,9 @@ constexpr int kTileBytes = BM * BK * 2;        // 16 KiB
 constexpr int kEpiWarps = 8;                   // 2 warps per TMEM lane quarter, each takes half the columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;  // 320
 enum { EPI_CONV = 0, EPI_LINEAR = 1, EPI_PARTIAL = 2, EPI_BB = 3 };
-constexpr int kBuilderWarps = 4;                // A_IM2COL only: 128 threads assemble the A tiles in shared memory
-constexpr int kThreadsBuilder = kThreads + 32 * kBuilderWarps;   // 448
+constexpr int kBuilderWarps = 8;                // A_IM2COL only: 256 threads assemble the A tiles in shared memory
+constexpr int kBuilderSlots = 4;                // ring slots are owned by builder-warp PAIRS (64 rows each)
+constexpr int kThreadsBuilder = kThreads + 32 * kBuilderWarps;   // 576
 constexpr int kMaxHalo = 8;                     // A_IM2COL: halo ring depth (TMA latency of the small-row boxes is ~3 us)
 constexpr int kStgBytes = 32 * 64;               // one epilogue chunk: 32 rows x 32 bf16, dense, 64B-swizzled (TMA store box)
 constexpr int kStagingBytes = kEpiWarps * kStgBytes;   // 16 KiB: per-warp staging buffers of the epilogue
@@ -82,7 +83,7 @@ struct GemmParams {
     int halo_nb;         // the halo is fetched as halo_nb boxes of halo_ppb pixels x halo_h rows ("planes"): rows of
     int halo_ppb;        // halo_ppb*cin contiguous elements keep the TMA row count ~10x lower than per-pixel rows
     int dbg;             // debug experiments (ewvit_debug_set_flags): 1 = skip epilogue stores, 2 = skip activation, 4 = skip staging transpose
-    long long *trace;    // debug: clock64 stamps of CTA 0, [4 roles][64 tiles][4] (ewvit_debug_set_trace)
+    long long *trace;    // debug: clock64 stamps of CTA 0, [6 roles][64 tiles][4] (ewvit_debug_set_trace)
     int plane_bytes;     // distance between planes in shared memory (128-byte aligned, >= halo_h*halo_ppb*cin*2)
 };
 
@@ -142,6 +143,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t kTmemColsT = kAccStages * kBN;
     __shared__ __align__(16) float s_scale[2 * kBN], s_shift[2 * kBN];
     __shared__ int s_koff[kBuilder ? 9 * 8 : 1];
+    __shared__ __align__(16) uint32_t s_zero[4];
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler, too
     const int lane = threadIdx.x & 31;
@@ -152,7 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ewvit::tma_prefetch_desc(&tmA);
         ewvit::tma_prefetch_desc(&tmB);
         for (int s = 0; s < kStages; ++s) {
-            ewvit::mbar_init(ewvit::smem_u32(&full[s]), (kBuilder && !p.b_res) ? 2 : 1);
+            ewvit::mbar_init(ewvit::smem_u32(&full[s]), kBuilder ? (p.b_res ? 2 : 3) : 1);   // [TMA B] + two builder halves
             ewvit::mbar_init(ewvit::smem_u32(&empty[s]), 1);
         }
         for (int a = 0; a < kAccStages; ++a) {
@@ -316,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // the same for every tile, so the divisions are done once
         for (int i = btid; i < p.num_kb * 8; i += 32 * kBuilderWarps) {
             const int k = i * 8;
-            int off = -1;
+            int off = 3 << 28;                                               // dx code 3 = zero padding of the K axis
             if (k < 9 * p.cin) {
                 const int tap = k / p.cin, c = k - tap * p.cin;
                 const int dy = tap / 3, dx = tap - dy * 3;
@@ -324,11 +326,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             s_koff[i] = off;
         }
+        if (btid < 4) s_zero[btid] = 0u;
+        const uint32_t zero_addr = ewvit::smem_u32(s_zero);
         asm volatile("bar.sync 3, %0;" ::"n"(32 * kBuilderWarps) : "memory");   // ids 1,2 belong to the epilogue groups
-        uint32_t row_src[4][3], row_dst[4], row_sw[4];   // row_src[rr][dx]: halo byte offset of pixel (py*s, px*s + dx)
+        uint32_t row_src[2][3], row_dst[2], row_sw[2];   // row_src[rr][dx]: halo byte offset of pixel (py*s, px*s + dx)
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const int row = lane + 32 * rr;
+        for (int rr = 0; rr < 2; ++rr) {
+            const int row = (bwarp >> 2) * 64 + lane + 32 * rr;
             const int py = row / p.box_w, px = row - py * p.box_w;
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
@@ -342,44 +346,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t g = 0;      // k-blocks seen so far by this CTA (all builder warps count the same sequence)
         int hb = 0;
         uint32_t hphase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int tt = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tt) {
             const int sp = (w / p.tiles_m) / p.tiles_n;
             const int kb0 = sp * p.kb_per_split;
             const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             ewvit::mbar_wait(ewvit::smem_u32(&hfull[hb]), hphase);
+            if (bwarp == 0 && lane == 0) EWVIT_TRACE(4, tt, 0);
             const uint32_t halo = smem_base + nstages * kStageB + hb * p.halo_stride;
             for (int kb = kb0; kb < kb1; ++kb, ++g) {
                 // every ring slot is owned by ONE builder warp, so consecutive uses of a slot are ordered by that warp's
                 // own waits (two warps sharing a slot could run two phases apart, which a parity wait cannot see)
                 const int stage = (int)(g % (uint32_t)nstages);
-                if ((stage & (kBuilderWarps - 1)) != bwarp) continue;
+                if ((stage & (kBuilderSlots - 1)) != (bwarp & (kBuilderSlots - 1))) continue;
                 const uint32_t phase = (g / (uint32_t)nstages) & 1u;
-                ewvit::mbar_wait(ewvit::smem_u32(&empty[stage]), phase ^ 1);
                 const uint32_t a_base = smem_base + stage * kStageB;
+                // the 8 chunk offsets of this k-block are the same for all 128 rows: read the table once
+                int off[8];
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                    uint4 v[8];
+                for (int j = 0; j < 8; ++j) off[j] = s_koff[kb * 8 + j];
+                {
+                    const int half = bwarp >> 2;          // this warp's 64 rows of the tile
+                    uint4 v[2][8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int off = s_koff[kb * 8 + j];
-                        v[j] = make_uint4(0u, 0u, 0u, 0u);
-                        if (off >= 0) {
-                            const int dx = off >> 28;
-                            const uint32_t src = dx == 0 ? row_src[rr][0] : (dx == 1 ? row_src[rr][1] : row_src[rr][2]);
-                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w)
-                                         : "r"(halo + src + (uint32_t)(off & 0x0FFFFFFF)));
+                    for (int r2 = 0; r2 < 2; ++r2) {
+                        const int rr = r2;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            // branch-free gather (predicated selects in PTX: the C++ ternaries compiled to ~3 branches
+                            // per chunk, ~1300 cycles per k-block); padding chunks read a 16-byte block of zeros instead
+                            asm("{\n\t.reg .pred q1, q2, q3;\n\t.reg .u32 a;\n\t"
+                                "setp.ge.s32 q1, %4, 1;\n\tsetp.ge.s32 q2, %4, 2;\n\tsetp.eq.s32 q3, %4, 3;\n\t"
+                                "selp.u32 a, %6, %5, q1;\n\tselp.u32 a, %7, a, q2;\n\tadd.u32 a, a, %8;\n\tselp.u32 a, %9, a, q3;\n\t"
+                                "ld.shared.v4.u32 {%0, %1, %2, %3}, [a];\n\t}"
+                                : "=r"(v[r2][j].x), "=r"(v[r2][j].y), "=r"(v[r2][j].z), "=r"(v[r2][j].w)
+                                : "r"(off[j] >> 28), "r"(row_src[rr][0]), "r"(row_src[rr][1]), "r"(row_src[rr][2]),
+                                  "r"(halo + (uint32_t)(off[j] & 0x0FFFFFFF)), "r"(zero_addr)
+                                : "memory");
                         }
                     }
+                    // the gathers above are in flight while we wait for the ring slot to drain
+                    (void)half;
+                    {
+                        if (bwarp == 0 && lane == 0) EWVIT_TRACE(4, tt, 1);
+                        ewvit::mbar_wait(ewvit::smem_u32(&empty[stage]), phase ^ 1);
+                        if (bwarp == 0 && lane == 0) EWVIT_TRACE(4, tt, 2);
+                    }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + row_dst[rr] + (((uint32_t)j ^ row_sw[rr]) << 4)),
-                                     "r"(v[j].x), "r"(v[j].y), "r"(v[j].z), "r"(v[j].w)
-                                     : "memory");
+                    for (int r2 = 0; r2 < 2; ++r2) {
+                        const int rr = r2;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + row_dst[rr] + (((uint32_t)j ^ row_sw[rr]) << 4)),
+                                         "r"(v[r2][j].x), "r"(v[r2][j].y), "r"(v[r2][j].z), "r"(v[r2][j].w)
+                                         : "memory");
+                    }
                 }
                 ewvit::fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) ewvit::mbar_arrive(ewvit::smem_u32(&full[stage]));
+                if (bwarp == 0 && lane == 0) EWVIT_TRACE(4, tt, 3);
             }
             __syncwarp();
             if (lane == 0) ewvit::mbar_arrive(ewvit::smem_u32(&hempty[hb]));
@@ -993,7 +1019,7 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
 }
 
 // Debug aid: when non-NULL, CTA 0 of every subsequent GEMM/conv launch writes clock64 stamps of its warp roles
-// to this device buffer ([4 roles][64 tiles][4] int64).  Not part of the hot path; pass NULL to switch it off.
+// to this device buffer ([6 roles][64 tiles][4] int64).  Not part of the hot path; pass NULL to switch it off.
 extern "C" int ewvit_debug_set_flags(int flags) {
     g_dbg = flags;
     return EWVIT_OK;

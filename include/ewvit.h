@@ -230,7 +230,7 @@ EWVIT_API int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const float
                                        const float *b2, int n, int hw, int c, int sq, float *gate_ws, void *stream);
 
 /* Debug aid for kernel bring-up: when non-NULL, CTA 0 of every subsequent tensor-core GEMM/conv launch writes
- * clock64 stamps of its warp roles to this device buffer ([4 roles][64 tiles][4] int64).  NULL switches it off. */
+ * clock64 stamps of its warp roles to this device buffer ([6 roles][64 tiles][4] int64).  NULL switches it off. */
 EWVIT_API int ewvit_debug_set_trace(void *device_buffer);
 
 /* Debug experiments on the tensor-core kernel's epilogue (bit 0: skip the global stores, bit 1: skip the

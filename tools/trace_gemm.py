@@ -18,17 +18,17 @@ def run(name, fn):
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
-    buf = torch.zeros(4 * 64 * 4, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(6 * 64 * 4, dtype=torch.int64, device="cuda")
     lib.ewvit_debug_set_trace(buf.data_ptr())
     fn()
     torch.cuda.synchronize()
     lib.ewvit_debug_set_trace(None)
-    t = buf.cpu().view(4, 64, 4)
+    t = buf.cpu().view(6, 64, 4)
     t0 = int(t[t > 0].min())
     print(f"=== {name}")
     for tile in range(8, 13):
         row = []
-        for role, nm in enumerate(("tma", "mma", "epi0", "epi1")):
+        for role, nm in enumerate(("tma", "mma", "epi0", "epi1", "bld0", "x")):
             v = t[role, tile]
             if int(v.max()) == 0:
                 continue
