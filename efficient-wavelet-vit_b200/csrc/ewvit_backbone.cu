@@ -4,7 +4,7 @@
 // into the epilogue, so an activation tensor is written once and read once -- the eager cuDNN path spends >50 % of
 // its device time in separate elementwise passes (profiles/r01_bench_launches.md).  All tensors NHWC bf16,
 // BatchNorm (eval) folded into the weights/bias on the host.
-#include "ewvit_common.cuh"
+#include "ewvit_tc.cuh"
 
 namespace {
 
@@ -60,161 +60,220 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict_
 }
 
 // ---- depthwise 3x3 (stride 1|2, pad 1) + bias + SiLU, and the squeeze (spatial mean) of the result.
-//      One CTA owns a channel slab (SC = 64 or 32 channels) of `fpc` consecutive frames.  Each frame's input plane
-//      for the slab is staged in shared memory with coalesced 16-byte cp.async copies, double-buffered so the next
-//      frame streams in while the current one is computed; thread = (pixel lane, 8-channel group) keeps its 72
-//      weights in registers for all frames and reads its 9 taps from shared memory (LDS.128, a quarter-warp reads
-//      128 contiguous bytes: conflict-free); the squeeze needs no atomics.
-template <int SC>
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ x, const float *__restrict__ w,
-                                                        const float *__restrict__ bias, __nv_bfloat16 *__restrict__ y,
-                                                        float *__restrict__ pooled, int n, int h, int wd, int ho, int wo,
-                                                        int c, int stride, int fpc, int fb) {
-    // fb = frames staged and processed together (small planes: 4 frames of 7x7 keep all pixel lanes busy and
-    // amortise the barriers); fpc = frames per CTA (multiple of fb)
-    constexpr int G = SC / 8;            // 8-channel groups per slab
-    constexpr int PL = 256 / G;          // pixel lanes
-    extern __shared__ __align__(16) unsigned char dw_smem[];
-    const int plane = h * wd * SC;                                                      // elements of one frame's slab
-    __nv_bfloat16 *s_in = reinterpret_cast<__nv_bfloat16 *>(dw_smem);                  // [2][fb][h*wd][SC]
-    float *s_w = reinterpret_cast<float *>(dw_smem + (size_t)2 * fb * plane * 2);       // [9][SC] then bias [SC]
-    float *s_sum = s_w + 10 * SC;                                                       // [fb][PL][SC + 1]
-    const int slabs = c / SC;
-    const int cs = (blockIdx.x % slabs) * SC;
-    const int f0 = (blockIdx.x / slabs) * fpc;
-    const int f1 = min(n, f0 + fpc);
+//      Work unit = (channel slab of SC = 64|32 channels, pass of `fb` consecutive frames).  Persistent CTAs (two per
+//      SM) each take a contiguous range of units, slab-major, so the grid has no partial last wave and a CTA reloads
+//      its weights at most once or twice.  One TMA box per unit brings the slab's input planes INCLUDING the one-pixel
+//      zero border into shared memory (out-of-range box coordinates are zero-filled by the TMA unit), double-buffered
+//      so the next unit streams in under the compute of the current one.  A work item = (frame, output column,
+//      4-channel group): the thread walks down its column with a sliding 3x3 window of fp32 registers, so every staged
+//      value is converted once per column (3 conversions per output instead of 9), the loop has no bounds checks or
+//      index divisions, and the 36 weights stay in registers.  The squeeze needs no atomics: column sums meet in
+//      shared memory.  SiLU(v) = h*tanh(h) + h with h = v/2: the 1/2 is folded into the weights and bias.
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+template <int SC, int STRIDE>
+__global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const float *__restrict__ w,
+                                                           const float *__restrict__ bias, __nv_bfloat16 *__restrict__ y,
+                                                           float *__restrict__ pooled, int n, int h, int wd, int ho, int wo,
+                                                           int c, int fb, int stage_bytes) {
+    constexpr int G = SC / 4;            // 4-channel groups per slab
+    extern __shared__ __align__(128) unsigned char dw_smem[];
+    // layout: [2 stages][fb][h+2][wd+2][SC] bf16 | weights [9][SC] + bias [SC] fp32 | column sums [2][fb][wo][SC] fp32 | 2 mbarriers
+    const uint32_t s_in = ewvit::smem_u32(dw_smem);
+    float *s_w = reinterpret_cast<float *>(dw_smem + (size_t)2 * stage_bytes);
+    float *s_sum = s_w + 10 * SC;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_sum + (size_t)2 * fb * wo * SC);
     const int tid = threadIdx.x;
+    const int slabs = c / SC;
+    const int passes = (n + fb - 1) / fb;
+    const long long units = (long long)slabs * passes;
+    const int u0 = (int)(units * blockIdx.x / gridDim.x), u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
     const int npix = ho * wo;
+    const int wp = wd + 2;
+    const int plane_bytes = (h + 2) * wp * SC * 2;
+    const uint32_t row_bytes = (uint32_t)wp * SC * 2;
 
-    auto stage_in = [&](int frame, int buf) {
-        const int nf = min(fb, f1 - frame);
-        for (int fl = 0; fl < nf; ++fl) {
-            const __nv_bfloat16 *px = x + (long long)(frame + fl) * h * wd * c + cs;
-            __nv_bfloat16 *dstb = s_in + ((size_t)buf * fb + fl) * plane;
-            for (int i = tid; i < h * wd * G; i += 256) {
-                const int p = i / G, g = i - p * G;
-                const uint32_t dst = ewvit::smem_u32(dstb + p * SC + g * 8);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(px + (long long)p * c + g * 8) : "memory");
-            }
+    if (tid == 0) {
+        if (s_in & 127u) __trap();          // TMA destination alignment
+        ewvit::mbar_init(ewvit::smem_u32(&s_bar[0]), 1);
+        ewvit::mbar_init(ewvit::smem_u32(&s_bar[1]), 1);
+        ewvit::mbar_fence_init();
+        ewvit::fence_proxy_async();
+        if (u0 < u1) {
+            ewvit::mbar_expect_tx(ewvit::smem_u32(&s_bar[0]), (uint32_t)fb * plane_bytes);
+            ewvit::tma_load_4d(s_in, &tmX, (u0 / passes) * SC, -1, -1, (u0 % passes) * fb, ewvit::smem_u32(&s_bar[0]));
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    stage_in(f0, 0);
-    for (int i = tid; i < 9 * SC; i += 256) s_w[i] = w[(i / SC) * c + cs + (i % SC)];
-    if (tid < SC) s_w[9 * SC + tid] = bias[cs + tid];
+    }
     __syncthreads();
-    const int g = tid % G, pl = tid / G;
-    float wr[9][8], br[8];
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) wr[t][j] = s_w[t * SC + g * 8 + j];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) br[j] = s_w[9 * SC + g * 8 + j];
 
-    int buf = 0;
-    for (int f = f0; f < f1; f += fb, buf ^= 1) {
-        const int nf = min(fb, f1 - f);
-        if (f + fb < f1) {
-            stage_in(f + fb, buf ^ 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int items = fb * wo * G;
+    const float inv_npix = 1.f / (float)npix;
+    const long long ystep = (long long)wo * c;
+    int buf = 0, cur_slab = -1;
+    uint32_t phases = 0u;
+    for (int u = u0; u < u1; ++u, buf ^= 1) {
+        const int slab = u / passes;
+        const int f = (u - slab * passes) * fb;
+        const int cs = slab * SC;
+        if (tid == 0 && u + 1 < u1) {      // the other buffer was released by the barrier that ended the previous unit
+            const uint32_t bar = ewvit::smem_u32(&s_bar[buf ^ 1]);
+            ewvit::mbar_expect_tx(bar, (uint32_t)fb * plane_bytes);
+            ewvit::tma_load_4d(s_in + (uint32_t)(buf ^ 1) * stage_bytes, &tmX, ((u + 1) / passes) * SC, -1, -1, ((u + 1) % passes) * fb, bar);
         }
-        __syncthreads();
-        float sum[8];
+        if (slab != cur_slab) {             // CTA-uniform; everyone left the previous unit's item loop at its closing barrier
+            for (int i = tid; i < 9 * SC; i += 256) s_w[i] = 0.5f * w[(i / SC) * c + cs + (i % SC)];
+            if (tid < SC) s_w[9 * SC + tid] = 0.5f * bias[cs + tid];
+            cur_slab = slab;
+            __syncthreads();
+        }
+        ewvit::mbar_wait(ewvit::smem_u32(&s_bar[buf]), (phases >> buf) & 1u);
+        phases ^= 1u << buf;
+        const uint32_t sb = s_in + (uint32_t)buf * stage_bytes;
+        float *ssum = s_sum + (size_t)buf * fb * wo * SC;
+        for (int item = tid; item < items; item += 256) {
+            const int g = item % G;
+            const int t = item / G;
+            const int ox = t % wo, fl = t / wo;
+            float wr[9][4], br[4], sum[4];
+            const uint32_t wbase = ewvit::smem_u32(s_w) + g * 16;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum[j] = 0.f;
-        int cur_fl = 0;
-        for (int item = pl; item < nf * npix; item += PL) {
-            const int fl = item / npix, o = item - fl * npix;
-            if (fl != cur_fl) {      // this thread's items moved on to the next frame: park the finished partial sum
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { s_sum[(cur_fl * PL + pl) * (SC + 1) + g * 8 + j] = sum[j]; sum[j] = 0.f; }
-                cur_fl = fl;
+            for (int k = 0; k < 9; ++k) {
+                const float4 v = lds128f(wbase + k * SC * 4);
+                wr[k][0] = v.x; wr[k][1] = v.y; wr[k][2] = v.z; wr[k][3] = v.w;
             }
-            const int oy = o / wo, ox = o - oy * wo;
-            const __nv_bfloat16 *sp = s_in + ((size_t)buf * fb + fl) * plane + g * 8;
-            float a[8];
+            {
+                const float4 v = lds128f(wbase + 9 * SC * 4);
+                br[0] = v.x; br[1] = v.y; br[2] = v.z; br[3] = v.w;
+            }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = br[j];
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                const int iy = oy * stride + dy - 1;
-                if (iy < 0 || iy >= h) continue;
+            for (int j = 0; j < 4; ++j) sum[j] = 0.f;
+            uint32_t rp = sb + (uint32_t)fl * plane_bytes + (uint32_t)(ox * STRIDE) * (SC * 2) + g * 8;   // padded (row 0, first tap column)
+            const bool live = f + fl < n;
+            __nv_bfloat16 *py = y + ((long long)(f + fl) * npix + ox) * c + cs + g * 4;
+            auto load_row = [&](float (&r)[3][4]) {      // the next padded row of this column's three taps
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
-                    const int ix = ox * stride + dx - 1;
-                    if (ix < 0 || ix >= wd) continue;
-                    const uint4 v = *reinterpret_cast<const uint4 *>(sp + (iy * wd + ix) * SC);
-                    const __nv_bfloat162 *vp = reinterpret_cast<const __nv_bfloat162 *>(&v);
+                    const uint2 v = lds64(rp + dx * (SC * 2));
+                    r[dx][0] = __uint_as_float(v.x << 16);
+                    r[dx][1] = __uint_as_float(v.x & 0xffff0000u);
+                    r[dx][2] = __uint_as_float(v.y << 16);
+                    r[dx][3] = __uint_as_float(v.y & 0xffff0000u);
+                }
+                rp += row_bytes;
+            };
+            auto emit = [&](const float (&r0)[3][4], const float (&r1)[3][4], const float (&r2)[3][4]) {
+                float a[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 fv = __bfloat1622float2(vp[j]);
-                        a[2 * j] = fmaf(wr[dy * 3 + dx][2 * j], fv.x, a[2 * j]);
-                        a[2 * j + 1] = fmaf(wr[dy * 3 + dx][2 * j + 1], fv.y, a[2 * j + 1]);
+                for (int j = 0; j < 4; ++j) {
+                    float hv = br[j];                   // h = v/2 (weights and bias are pre-halved)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        hv = fmaf(wr[dx][j], r0[dx][j], hv);
+                        hv = fmaf(wr[3 + dx][j], r1[dx][j], hv);
+                        hv = fmaf(wr[6 + dx][j], r2[dx][j], hv);
                     }
+                    float th;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hv));
+                    a[j] = fmaf(hv, th, hv);
+                    sum[j] += a[j];
+                }
+                if (live) {
+                    const __nv_bfloat162 p0 = __floats2bfloat162_rn(a[0], a[1]), p1 = __floats2bfloat162_rn(a[2], a[3]);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t *>(&p0);
+                    pk.y = *reinterpret_cast<const uint32_t *>(&p1);
+                    *reinterpret_cast<uint2 *>(py) = pk;
+                }
+                py += ystep;
+            };
+            float ra[3][4], rb[3][4], rc[3][4];
+            if (STRIDE == 1) {
+                load_row(ra);
+                load_row(rb);
+                for (int oy = 0; oy < ho; oy += 3) {
+                    load_row(rc);
+                    emit(ra, rb, rc);
+                    if (oy + 1 < ho) { load_row(ra); emit(rb, rc, ra); }
+                    if (oy + 2 < ho) { load_row(rb); emit(rc, ra, rb); }
+                }
+            } else {
+                load_row(ra);
+                for (int oy = 0; oy < ho; oy += 2) {
+                    load_row(rb);
+                    load_row(rc);
+                    emit(ra, rb, rc);
+                    if (oy + 1 < ho) { load_row(rb); load_row(ra); emit(rc, rb, ra); }
                 }
             }
-            uint4 pk;
-            __nv_bfloat162 *pp = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                pp[j] = __floats2bfloat162_rn(silu(a[2 * j]), silu(a[2 * j + 1]));
-                const float2 r = __bfloat1622float2(pp[j]);   // pool what is actually stored
-                sum[2 * j] += r.x;
-                sum[2 * j + 1] += r.y;
-            }
-            *reinterpret_cast<uint4 *>(y + ((long long)(f + fl) * npix + o) * c + cs + g * 8) = pk;
+            *reinterpret_cast<float4 *>(ssum + (fl * wo + ox) * SC + g * 4) = make_float4(sum[0], sum[1], sum[2], sum[3]);
         }
+        __syncthreads();    // column sums are complete and everyone is done reading this stage buffer
         if (pooled) {
-            // every (frame, pixel lane) slot is written exactly once: by the flush above, here, or as an explicit zero
-            for (int fl = 0; fl < nf; ++fl) {
-                const bool mine = fl == cur_fl, later = fl > cur_fl;
-                if (mine || later) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) s_sum[(fl * PL + pl) * (SC + 1) + g * 8 + j] = mine ? sum[j] : 0.f;
-                }
-            }
-            __syncthreads();
-            for (int i = tid; i < nf * SC; i += 256) {
+            for (int i = tid; i < fb * SC; i += 256) {
                 const int fl = i / SC, ch = i - fl * SC;
+                if (f + fl >= n) continue;
                 float t = 0.f;
-                for (int k = 0; k < PL; ++k) t += s_sum[(fl * PL + k) * (SC + 1) + ch];
-                pooled[(long long)(f + fl) * c + cs + ch] = t / (float)npix;
+                for (int k = 0; k < wo; ++k) t += ssum[(fl * wo + k) * SC + ch];
+                pooled[(long long)(f + fl) * c + cs + ch] = t * inv_npix;
             }
         }
-        __syncthreads();   // everyone is done with this stage buffer (and s_sum) before it is refilled
     }
 }
 
 // ---- squeeze-excitation gate: gate[n, c] = sigmoid(W2 * silu(W1 * pooled[n] + b1) + b2).
-//      One CTA serves kSeF frames so every weight row is read from L2 once per kSeF frames (the two FC matrices are
-//      ~0.8 MB at c = 1536: one-frame CTAs made the 512-frame launch read 400 MB of weights).
-constexpr int kSeF = 1;
-__global__ void __launch_bounds__(256) se_gate_kernel(const float *__restrict__ pooled, const float *__restrict__ w1,
-                                                      const float *__restrict__ b1, const float *__restrict__ w2t,
-                                                      const float *__restrict__ b2, float *__restrict__ gate, int n, int c, int sq) {
-    extern __shared__ float se_sm[];
+//      One CTA serves kSeF frames, so each weight matrix (up to 0.4 MB at c = 1536) is pulled from L2 once per kSeF
+//      frames; both layers read the weights as float4 with several independent loads in flight per thread (the
+//      first version was a chain of dependent L2 round trips: ~50 us per launch for ~1 MFLOP).
+constexpr int kSeF = 4;
+constexpr int kSeThreads = 512;
+constexpr int kSeMaxC = 12 * 128;          // FC1 keeps one weight row (c / 128 float4 per lane) in registers
+__global__ void __launch_bounds__(kSeThreads) se_gate_kernel(const float *__restrict__ pooled, const float *__restrict__ w1,
+                                                             const float *__restrict__ b1, const float *__restrict__ w2t,
+                                                             const float *__restrict__ b2, float *__restrict__ gate, int n, int c, int sq) {
+    extern __shared__ __align__(16) float se_sm[];
     float *s_pool = se_sm;                 // [kSeF][c]
     float *s_hid = se_sm + kSeF * c;       // [kSeF][sq]
     const int f0 = blockIdx.x * kSeF;
     const int nf = min(kSeF, n - f0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < kSeF * c; i += 256) {
-        const int f = i / c;
-        s_pool[i] = f < nf ? pooled[(long long)(f0 + f) * c + (i - f * c)] : 0.f;
+    const int c4 = c >> 2;
+    for (int i = tid; i < kSeF * c4; i += kSeThreads) {
+        const int f = i / c4;
+        reinterpret_cast<float4 *>(s_pool)[i] =
+            f < nf ? __ldg(reinterpret_cast<const float4 *>(pooled + (long long)(f0 + f) * c) + (i - f * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    for (int j = warp; j < sq; j += 8) {
+    for (int j = warp; j < sq; j += kSeThreads / 32) {
+        // the whole weight row is requested before the first use: one L2 round trip per row instead of one per few loads
+        const float4 *wrow = reinterpret_cast<const float4 *>(w1 + (long long)j * c);
+        float4 wv[kSeMaxC / 128];
+#pragma unroll
+        for (int i = 0; i < kSeMaxC / 128; ++i) {
+            const int k = lane + 32 * i;
+            wv[i] = k < c4 ? __ldg(wrow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float acc[kSeF];
 #pragma unroll
         for (int f = 0; f < kSeF; ++f) acc[f] = 0.f;
-#pragma unroll 4
-        for (int k = lane; k < c; k += 32) {
-            const float wv = w1[(long long)j * c + k];
 #pragma unroll
-            for (int f = 0; f < kSeF; ++f) acc[f] = fmaf(wv, s_pool[f * c + k], acc[f]);
+        for (int i = 0; i < kSeMaxC / 128; ++i) {
+            const int k = lane + 32 * i;
+            if (k < c4) {
+#pragma unroll
+                for (int f = 0; f < kSeF; ++f) {
+                    const float4 pv = reinterpret_cast<const float4 *>(s_pool + f * c)[k];
+                    acc[f] = fmaf(wv[i].x, pv.x, fmaf(wv[i].y, pv.y, fmaf(wv[i].z, pv.z, fmaf(wv[i].w, pv.w, acc[f]))));
+                }
+            }
         }
 #pragma unroll
         for (int f = 0; f < kSeF; ++f) {
@@ -225,20 +284,40 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float *__restrict__ 
         }
     }
     __syncthreads();
-    for (int i = tid; i < c; i += 256) {
-        float acc[kSeF];
-        const float bb = b2[i];
+    for (int i = tid; i < c4; i += kSeThreads) {          // 4 consecutive channels per thread
+        float4 acc[kSeF];
+        const float4 bb = __ldg(reinterpret_cast<const float4 *>(b2) + i);
 #pragma unroll
         for (int f = 0; f < kSeF; ++f) acc[f] = bb;
-#pragma unroll 8
-        for (int j = 0; j < sq; ++j) {
-            const float wv = w2t[(long long)j * c + i];
+        for (int j0 = 0; j0 < sq; j0 += 16) {
+            float4 wv[16];
 #pragma unroll
-            for (int f = 0; f < kSeF; ++f) acc[f] = fmaf(wv, s_hid[f * sq + j], acc[f]);
+            for (int u = 0; u < 16; ++u)
+                wv[u] = j0 + u < sq ? __ldg(reinterpret_cast<const float4 *>(w2t + (long long)(j0 + u) * c) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                if (j0 + u < sq) {
+#pragma unroll
+                    for (int f = 0; f < kSeF; ++f) {
+                        const float hv = s_hid[f * sq + j0 + u];
+                        acc[f].x = fmaf(wv[u].x, hv, acc[f].x);
+                        acc[f].y = fmaf(wv[u].y, hv, acc[f].y);
+                        acc[f].z = fmaf(wv[u].z, hv, acc[f].z);
+                        acc[f].w = fmaf(wv[u].w, hv, acc[f].w);
+                    }
+                }
+            }
         }
 #pragma unroll
         for (int f = 0; f < kSeF; ++f)
-            if (f < nf) gate[(long long)(f0 + f) * c + i] = 1.f / (1.f + __expf(-acc[f]));
+            if (f < nf) {
+                float4 o;
+                o.x = 1.f / (1.f + __expf(-acc[f].x));
+                o.y = 1.f / (1.f + __expf(-acc[f].y));
+                o.z = 1.f / (1.f + __expf(-acc[f].z));
+                o.w = 1.f / (1.f + __expf(-acc[f].w));
+                reinterpret_cast<float4 *>(gate + (long long)(f0 + f) * c)[i] = o;
+            }
     }
 }
 
@@ -281,6 +360,22 @@ extern "C" int ewvit_stem_conv_fwd(const float *x, int n, int h, int wd, const f
     return EWVIT_OK;
 }
 
+template <int SC, int STRIDE>
+static int launch_dw(const CUtensorMap &tm, const float *w, const float *bias, void *y, float *pooled, int n, int h, int wd, int ho,
+                     int wo, int c, int fb, int stage_bytes, size_t smem, unsigned grid, cudaStream_t stream) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    EWVIT_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(dwconv3x3_kernel<SC, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    dwconv3x3_kernel<SC, STRIDE><<<grid, 256, smem, stream>>>(tm, w, bias, static_cast<__nv_bfloat16 *>(y), pooled, n, h, wd, ho, wo, c,
+                                                             fb, stage_bytes);
+    EWVIT_LAUNCH_OK();
+    return EWVIT_OK;
+}
+
 extern "C" int ewvit_dwconv3x3_nhwc_bf16(const void *x, const float *w, const float *bias, int n, int h, int wd, int c,
                                          int stride, void *y, float *pooled, void *stream) {
     EWVIT_REQUIRE(n >= 0 && h > 0 && wd > 0 && c > 0, EWVIT_ERR_INVALID_ARG, "ewvit_dwconv3x3_nhwc_bf16: bad sizes");
@@ -289,47 +384,49 @@ extern "C" int ewvit_dwconv3x3_nhwc_bf16(const void *x, const float *w, const fl
                   "ewvit_dwconv3x3_nhwc_bf16: NULL or misaligned pointer");
     EWVIT_REQUIRE(c % 64 == 0 && (stride == 1 || stride == 2), EWVIT_ERR_UNSUPPORTED,
                   "ewvit_dwconv3x3_nhwc_bf16: needs c %% 64 == 0 and stride 1|2 (got c=%d stride=%d)", c, stride);
+    EWVIT_REQUIRE(h + 2 <= 256 && wd + 2 <= 256, EWVIT_ERR_UNSUPPORTED, "ewvit_dwconv3x3_nhwc_bf16: plane %dx%d exceeds the TMA box limit", h, wd);
     int rc = ewvit_check_device();
     if (rc != EWVIT_OK) return rc;
     const int ho = (h - 1) / stride + 1, wo = (wd - 1) / stride + 1;
-    // 64-channel slabs when the staged input plane fits ~56 KB of shared memory, else 32-channel slabs
-    const bool wide = (size_t)h * wd * 64 * 2 <= 50 * 1024;   // two stages of the slab's input plane
+    // 64-channel slabs when two stages of the padded input plane fit ~100 KB of shared memory (two CTAs per SM), else 32
+    const size_t plane64 = (size_t)(h + 2) * (wd + 2) * 64 * 2;
+    const bool wide = 2 * plane64 <= 100 * 1024;
     const int sc = wide ? 64 : 32;
-    int fb = 1;                                                // frames processed together (small planes)
-    while (fb < 4 && (size_t)h * wd * sc * 2 * (fb * 2) <= 26 * 1024 && n % (fb * 2) == 0) fb *= 2;
-    const size_t smem = (size_t)2 * fb * h * wd * sc * 2 + (size_t)10 * sc * 4 + (size_t)fb * (256 / (sc / 8)) * (sc + 1) * 4;
-    EWVIT_REQUIRE(smem <= 200 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_dwconv3x3_nhwc_bf16: %dx%d input plane too large for the staged kernel", h, wd);
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    EWVIT_CUDA_OK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        EWVIT_CUDA_OK(cudaFuncSetAttribute(dwconv3x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        EWVIT_CUDA_OK(cudaFuncSetAttribute(dwconv3x3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    const size_t plane = (size_t)(h + 2) * (wd + 2) * sc * 2;
+    EWVIT_REQUIRE(2 * plane <= 190 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_dwconv3x3_nhwc_bf16: %dx%d input plane too large for the staged kernel", h, wd);
+    // frames per pass: enough (frame, column, channel group) items for the 256 threads, within ~48 KB per stage
+    int fb = 1;
+    while (fb < 8 && fb * wo * (sc / 4) < 224 && 2 * fb * plane <= 48 * 1024 && fb * 2 <= n) fb *= 2;
+    const int stage_bytes = (int)(((size_t)fb * plane + 127) / 128 * 128);
+    const size_t smem = (size_t)2 * stage_bytes + (size_t)10 * sc * 4 + (size_t)2 * fb * wo * sc * 4 + 16;
+    EWVIT_REQUIRE(smem <= 200 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_dwconv3x3_nhwc_bf16: %dx%d needs %zu bytes of shared memory", h, wd, smem);
+    const long long units = (long long)(c / sc) * ((n + fb - 1) / fb);
+    long long grid = 2LL * ewvit_num_sms();
+    if (grid > units) grid = units;
+    CUtensorMap tm;
+    const uint64_t dims[4] = {(uint64_t)c, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[4] = {2, (uint64_t)c * 2, (uint64_t)wd * c * 2, (uint64_t)h * wd * c * 2};
+    const uint32_t box[4] = {(uint32_t)sc, (uint32_t)(wd + 2), (uint32_t)(h + 2), (uint32_t)fb};
+    rc = ewvit_make_tmap_bf16(&tm, x, 4, dims, strides, box, nullptr, /*swizzle128=*/false);
+    if (rc != EWVIT_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (wide) {
+        if (stride == 1) return launch_dw<64, 1>(tm, w, bias, y, pooled, n, h, wd, ho, wo, c, fb, stage_bytes, smem, (unsigned)grid, st);
+        return launch_dw<64, 2>(tm, w, bias, y, pooled, n, h, wd, ho, wo, c, fb, stage_bytes, smem, (unsigned)grid, st);
     }
-    // frames per CTA: amortise the weight prologue while keeping >= ~4 CTAs per SM in the grid
-    int fpc = 8;
-    while (fpc > fb && (long long)((n + fpc - 1) / fpc) * (c / sc) < 4LL * ewvit_num_sms()) fpc /= 2;
-    if (fpc < fb) fpc = fb;
-    const unsigned grid = (unsigned)((long long)((n + fpc - 1) / fpc) * (c / sc));
-    if (wide)
-        dwconv3x3_kernel<64><<<grid, 256, smem, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16 *>(x), w, bias,
-                                                                        static_cast<__nv_bfloat16 *>(y), pooled, n, h, wd, ho, wo, c, stride, fpc, fb);
-    else
-        dwconv3x3_kernel<32><<<grid, 256, smem, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16 *>(x), w, bias,
-                                                                        static_cast<__nv_bfloat16 *>(y), pooled, n, h, wd, ho, wo, c, stride, fpc, fb);
-    EWVIT_LAUNCH_OK();
-    return EWVIT_OK;
+    if (stride == 1) return launch_dw<32, 1>(tm, w, bias, y, pooled, n, h, wd, ho, wo, c, fb, stage_bytes, smem, (unsigned)grid, st);
+    return launch_dw<32, 2>(tm, w, bias, y, pooled, n, h, wd, ho, wo, c, fb, stage_bytes, smem, (unsigned)grid, st);
 }
 
 extern "C" int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const float *w1, const float *b1, const float *w2t,
                                         const float *b2, int n, int hw, int c, int sq, float *gate_ws, void *stream) {
     EWVIT_REQUIRE(n >= 0 && hw > 0 && c > 0 && sq > 0, EWVIT_ERR_INVALID_ARG, "ewvit_se_apply_nhwc_bf16: bad sizes");
     if (n == 0) return EWVIT_OK;
-    EWVIT_REQUIRE(x && pooled && w1 && b1 && w2t && b2 && gate_ws && ewvit_aligned16(x) && ewvit_aligned16(gate_ws), EWVIT_ERR_INVALID_ARG,
+    EWVIT_REQUIRE(x && pooled && w1 && b1 && w2t && b2 && gate_ws && ewvit_aligned16(x) && ewvit_aligned16(gate_ws) &&
+                      ewvit_aligned16(pooled) && ewvit_aligned16(w1) && ewvit_aligned16(w2t) && ewvit_aligned16(b2), EWVIT_ERR_INVALID_ARG,
                   "ewvit_se_apply_nhwc_bf16: NULL or misaligned pointer");
     const size_t gate_smem = (size_t)kSeF * (c + sq) * sizeof(float);
-    EWVIT_REQUIRE(c % 8 == 0 && gate_smem <= 160 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_se_apply_nhwc_bf16: c=%d sq=%d not supported", c, sq);
+    EWVIT_REQUIRE(c % 8 == 0 && c <= kSeMaxC && gate_smem <= 160 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_se_apply_nhwc_bf16: c=%d sq=%d not supported", c, sq);
     int rc = ewvit_check_device();
     if (rc != EWVIT_OK) return rc;
     static bool se_attr[64] = {false};
@@ -339,13 +436,37 @@ extern "C" int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const floa
         EWVIT_CUDA_OK(cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         if (dev >= 0 && dev < 64) se_attr[dev] = true;
     }
-    se_gate_kernel<<<(unsigned)((n + kSeF - 1) / kSeF), 256, gate_smem, (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, gate_ws, n, c, sq);
+    se_gate_kernel<<<(unsigned)((n + kSeF - 1) / kSeF), kSeThreads, gate_smem, (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, gate_ws, n, c, sq);
     EWVIT_LAUNCH_OK();
     const long long total8 = (long long)n * hw * (c / 8);
     long long blocks = (total8 + 255) / 256;
     const long long cap = (long long)ewvit_num_sms() * 16;
     if (blocks > cap) blocks = cap;
     se_scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(static_cast<__nv_bfloat16 *>(x), gate_ws, total8, hw, c / 8);
+    EWVIT_LAUNCH_OK();
+    return EWVIT_OK;
+}
+
+// Squeeze-excitation gate only (the scaling is fused into ewvit_conv1x1_gated_nhwc_bf16).
+extern "C" int ewvit_se_gate_fwd(const float *pooled, const float *w1, const float *b1, const float *w2t, const float *b2, int n,
+                                 int c, int sq, float *gate, void *stream) {
+    EWVIT_REQUIRE(n >= 0 && c > 0 && sq > 0, EWVIT_ERR_INVALID_ARG, "ewvit_se_gate_fwd: bad sizes");
+    if (n == 0) return EWVIT_OK;
+    EWVIT_REQUIRE(pooled && w1 && b1 && w2t && b2 && gate && ewvit_aligned16(gate) && ewvit_aligned16(pooled) &&
+                      ewvit_aligned16(w1) && ewvit_aligned16(w2t) && ewvit_aligned16(b2), EWVIT_ERR_INVALID_ARG,
+                  "ewvit_se_gate_fwd: NULL or misaligned pointer");
+    const size_t gate_smem = (size_t)kSeF * (c + sq) * sizeof(float);
+    EWVIT_REQUIRE(c % 8 == 0 && c <= kSeMaxC && gate_smem <= 160 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_se_gate_fwd: c=%d sq=%d not supported", c, sq);
+    int rc = ewvit_check_device();
+    if (rc != EWVIT_OK) return rc;
+    static bool se_attr[64] = {false};
+    int dev = 0;
+    EWVIT_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !se_attr[dev]) {
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        if (dev >= 0 && dev < 64) se_attr[dev] = true;
+    }
+    se_gate_kernel<<<(unsigned)((n + kSeF - 1) / kSeF), kSeThreads, gate_smem, (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, gate, n, c, sq);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }

@@ -41,7 +41,7 @@ constexpr int kOperandBytes = 200 * 1024;       // operand stages (+ halo buffer
 constexpr int kPayloadBytes = kOperandBytes + kStagingBytes;   // barriers live right behind       // operand stages (+ halo buffers); barriers live right behind
 constexpr int kSmemBytes = kPayloadBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 
-enum { A_FLAT = 0, A_TILE4D = 1, A_IM2COL = 2 };
+enum { A_FLAT = 0, A_TILE4D = 1, A_IM2COL = 2, A_SCALED = 3 };
 
 struct GemmParams {
     int a_mode;
@@ -77,6 +77,13 @@ struct GemmParams {
     int halo_bytes;      // bytes of one halo buffer (TMA transaction size)
     int halo_stride;     // 1024-aligned distance between consecutive halo buffers
     int halo_bufs;       // halo ring depth (<= kMaxHalo)
+    // A_SCALED (1x1 conv behind a squeeze-excitation block): the A tile arrives by TMA as for A_FLAT and builder warps
+    // multiply it in place by the per-(frame, channel) gate before the MMA consumes it, so the separate x *= gate
+    // pass (one read + one write of the expanded tensor) disappears; tile geometry = A_FLAT
+    const __nv_bfloat16 *a_ptr;
+    const float *a_gate;   // [frames, K] fp32
+    int a_hw;              // rows (pixels) per frame
+    int a_k;               // K = row pitch of A and of the gate
     int stage_bytes;     // ring slot size: A tile (+ B tile unless the weights are resident)
     int b_res;           // A_IM2COL: all k-blocks of B stay resident in shared memory (loaded once per CTA)
     int bres_off;        // byte offset of the resident B region
@@ -154,7 +161,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ewvit::tma_prefetch_desc(&tmA);
         ewvit::tma_prefetch_desc(&tmB);
         for (int s = 0; s < kStages; ++s) {
-            ewvit::mbar_init(ewvit::smem_u32(&full[s]), kBuilder ? (p.b_res ? 2 : 3) : 1);   // [TMA B] + two builder halves
+            ewvit::mbar_init(ewvit::smem_u32(&full[s]), !kBuilder ? 1 : p.a_mode == A_SCALED ? kBuilderWarps : (p.b_res ? 2 : 3));   // [TMA B] + two builder halves | all builder warps
             ewvit::mbar_init(ewvit::smem_u32(&empty[s]), 1);
         }
         for (int a = 0; a < kAccStages; ++a) {
@@ -207,13 +214,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int kb0 = sp * p.kb_per_split;
             const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             int tx = 0, ty = 0, img = 0;
-            if (p.a_mode != A_FLAT) {
+            if (p.a_mode == A_TILE4D || p.a_mode == A_IM2COL) {
                 tx = m_t % p.tiles_x;
                 const int t2 = m_t / p.tiles_x;
                 ty = t2 % p.tiles_y;
                 img = t2 / p.tiles_y;
             }
-            if (kBuilder) {
+            if (kBuilder && p.a_mode == A_IM2COL) {
                 // the tile's input halo (out-of-image pixels zero-filled) as a few wide boxes; then only B per k-block
                 ewvit::mbar_wait(ewvit::smem_u32(&hempty[hb]), hphase ^ 1);
                 const uint32_t hbar = ewvit::smem_u32(&hfull[hb]);
@@ -244,11 +251,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int ax0 = tx * p.box_w * p.in_stride, ay0 = ty * p.box_h * p.in_stride;
             for (int kb = kb0; kb < kb1; ++kb) {
                 ewvit::mbar_wait(ewvit::smem_u32(&empty[stage]), phase ^ 1);
-                const uint32_t bar = ewvit::smem_u32(&full[stage]);
+                // A_SCALED: the builders post-process the raw tile, so completion goes to the `raw` (halo) barrier
+                const uint32_t bar = ewvit::smem_u32((kBuilder && p.a_mode == A_SCALED) ? &hfull[stage] : &full[stage]);
                 const uint32_t a_dst = smem_base + stage * kStageB;
                 if (ewvit::elect_one()) {
                     ewvit::mbar_expect_tx(bar, kStageB);
-                    if (p.a_mode == A_FLAT)
+                    if (p.a_mode == A_FLAT || p.a_mode == A_SCALED)
                         ewvit::tma_load_2d(a_dst, &tmA, chunk * BK, m_t * BM + p.tap_a0[tap], bar);
                     else
                         ewvit::tma_load_4d(a_dst, &tmA, chunk * BK, ax0 + p.tap_a0[tap], ay0 + p.tap_a1[tap], img, bar);
@@ -314,6 +322,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // are in flight and the proxy fence of one overlaps the copies of the others.
         const int bwarp = warp - (2 + kEpiWarps);
         const int btid = threadIdx.x - 32 * (2 + kEpiWarps);
+        if (p.a_mode == A_SCALED) {
+            // The producer warp fetches the raw A tile (and B) by TMA exactly as for a plain 1x1 conv, but signals the
+            // `raw` barrier (the halo barriers, unused in this mode); the 256 builder threads multiply the tile by the
+            // squeeze-excitation gate IN PLACE (swizzled 16-byte chunks, 4 rows per thread) and only then hand the slot
+            // to the tensor core.  Global traffic stays asynchronous and the separate x *= gate pass is gone.
+            const int j = btid & 7;                 // 16-byte chunk (8 channels) of the 64-channel k-block
+            const int rbase = btid >> 3;            // rows rbase + 32 i, i = 0..3  (all have the same swizzle phase)
+            const uint32_t chunk_off = (uint32_t)rbase * 128u + (((uint32_t)j ^ (uint32_t)(rbase & 7)) << 4);
+            const int last_frame = (int)((p.M - 1) / p.a_hw);
+            uint32_t g = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int m_t = w % p.tiles_m;
+                const int sp = (w / p.tiles_m) / p.tiles_n;
+                const int kb0 = sp * p.kb_per_split;
+                const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                const float *gp[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const long long row = (long long)m_t * BM + rbase + 32 * i;
+                    const int fr = min((int)(row / p.a_hw), last_frame);     // rows past M are zero-filled by TMA
+                    gp[i] = p.a_gate + (long long)fr * p.a_k + j * 8;
+                }
+                for (int kb = kb0; kb < kb1; ++kb, ++g) {
+                    const int stage = (int)(g % (uint32_t)nstages);
+                    const uint32_t phase = (g / (uint32_t)nstages) & 1u;
+                    const bool kin = kb * BK + j * 8 < p.a_k;               // K tail: the tile holds zeros there
+                    float4 g0[4], g1[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        g0[i] = g1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (kin) {
+                            g0[i] = __ldg(reinterpret_cast<const float4 *>(gp[i] + kb * BK));
+                            g1[i] = __ldg(reinterpret_cast<const float4 *>(gp[i] + kb * BK) + 1);
+                        }
+                    }
+                    ewvit::mbar_wait(ewvit::smem_u32(&hfull[stage]), phase);
+                    const uint32_t a_base = smem_base + stage * kStageB + chunk_off;
+                    uint4 v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
+                                     : "r"(a_base + i * 32 * 128) : "memory");
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const __nv_bfloat162 *vp = reinterpret_cast<const __nv_bfloat162 *>(&v[i]);
+                        const float2 f0 = __bfloat1622float2(vp[0]), f1 = __bfloat1622float2(vp[1]);
+                        const float2 f2 = __bfloat1622float2(vp[2]), f3 = __bfloat1622float2(vp[3]);
+                        const __nv_bfloat162 o0 = __floats2bfloat162_rn(f0.x * g0[i].x, f0.y * g0[i].y);
+                        const __nv_bfloat162 o1 = __floats2bfloat162_rn(f1.x * g0[i].z, f1.y * g0[i].w);
+                        const __nv_bfloat162 o2 = __floats2bfloat162_rn(f2.x * g1[i].x, f2.y * g1[i].y);
+                        const __nv_bfloat162 o3 = __floats2bfloat162_rn(f3.x * g1[i].z, f3.y * g1[i].w);
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + i * 32 * 128),
+                                     "r"(*reinterpret_cast<const uint32_t *>(&o0)), "r"(*reinterpret_cast<const uint32_t *>(&o1)),
+                                     "r"(*reinterpret_cast<const uint32_t *>(&o2)), "r"(*reinterpret_cast<const uint32_t *>(&o3))
+                                     : "memory");
+                    }
+                    ewvit::fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) ewvit::mbar_arrive(ewvit::smem_u32(&full[stage]));
+                }
+            }
+        } else {
         // byte offset (relative to a pixel's halo origin) of every 16-byte chunk of the dense K axis, -1 = zero pad;
         // the same for every tile, so the divisions are done once
         for (int i = btid; i < p.num_kb * 8; i += 32 * kBuilderWarps) {
@@ -411,6 +481,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) ewvit::mbar_arrive(ewvit::smem_u32(&hempty[hb]));
             if (++hb == p.halo_bufs) { hb = 0; hphase ^= 1; }
         }
+        }   // A_IM2COL
     } else {
         // ---------------------------------------------------------------- epilogue (warps 2..9)
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -446,7 +517,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bool valid, zero = false;
             long long orow;
             int st_x = 0, st_y = 0, st_img = 0;     // TMA-store box origin of this warp's 32 rows (2 pixel rows x 16 pixels)
-            if (p.a_mode == A_FLAT) {
+            if (p.a_mode == A_FLAT || p.a_mode == A_SCALED) {
                 orow = (long long)m_t * BM + r;
                 valid = orow < p.M;
                 if (p.pad_hp > 0) {
@@ -518,7 +589,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (!(p.dbg & 1)) {
                         stage_chunk_bf16(stg, lane, pk);
                         if (lane == 0) {
-                            if (p.a_mode == A_FLAT) tma_store_2d(&tmC, stg, p.col_off + col0, m_t * BM + q * 32);
+                            if (p.a_mode == A_FLAT || p.a_mode == A_SCALED) tma_store_2d(&tmC, stg, p.col_off + col0, m_t * BM + q * 32);
                             else tma_store_4d(&tmC, stg, p.col_off + col0, st_x, st_y, st_img);
                         }
                     } else if (pk[0] == 0x12345678u) static_cast<uint32_t *>(p.out)[0] = pk[1];   // keep the math alive
@@ -576,7 +647,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     stage_chunk_bf16(stg, lane, pk);
                     if (lane == 0) {
-                        if (p.a_mode == A_FLAT) tma_store_2d(&tmC, stg, p.col_off + col0, m_t * BM + q * 32);
+                        if (p.a_mode == A_FLAT || p.a_mode == A_SCALED) tma_store_2d(&tmC, stg, p.col_off + col0, m_t * BM + q * 32);
                         else tma_store_4d(&tmC, stg, p.col_off + col0, st_x, st_y, st_img);
                     }
                 } else {
@@ -675,7 +746,7 @@ int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMa
                 int bn = BN) {
     if (epi == EPI_CONV) return launch_gemm_t<EPI_CONV, false, 128>(tmA, tmB, tmC, p, stream);
     if (epi == EPI_BB) {
-        if (p.a_mode == A_IM2COL)
+        if (p.a_mode == A_IM2COL || p.a_mode == A_SCALED)
             return bn == 256 ? launch_gemm_t<EPI_BB, true, 256>(tmA, tmB, tmC, p, stream) : launch_gemm_t<EPI_BB, true, 128>(tmA, tmB, tmC, p, stream);
         return bn == 256 ? launch_gemm_t<EPI_BB, false, 256>(tmA, tmB, tmC, p, stream) : launch_gemm_t<EPI_BB, false, 128>(tmA, tmB, tmC, p, stream);
     }
@@ -1028,4 +1099,54 @@ extern "C" int ewvit_debug_set_flags(int flags) {
 extern "C" int ewvit_debug_set_trace(void *device_buffer) {
     g_trace = static_cast<long long *>(device_buffer);
     return EWVIT_OK;
+}
+
+
+// 1x1 convolution behind a squeeze-excitation block: y = act(((x * gate[frame]) W^T) + bias) + residual, with the gate
+// applied while the A operand tile is assembled (no separate scaling pass over the expanded tensor).
+extern "C" int ewvit_conv1x1_gated_nhwc_bf16(const void *x, const float *gate, const void *w, int n, int hw, int cin, int cout,
+                                             const float *bias, int act, const void *residual, void *y, void *stream) {
+    EWVIT_REQUIRE(n >= 0 && hw > 0 && cin > 0 && cout > 0, EWVIT_ERR_INVALID_ARG, "ewvit_conv1x1_gated_nhwc_bf16: bad sizes");
+    if (n == 0) return EWVIT_OK;
+    EWVIT_REQUIRE(x && gate && w && y, EWVIT_ERR_INVALID_ARG, "ewvit_conv1x1_gated_nhwc_bf16: NULL pointer");
+    EWVIT_REQUIRE(cin % 8 == 0 && cout % 8 == 0, EWVIT_ERR_UNSUPPORTED,
+                  "ewvit_conv1x1_gated_nhwc_bf16: channel counts must be multiples of 8 (got cin=%d cout=%d)", cin, cout);
+    EWVIT_REQUIRE(act == 0 || act == 1 || act == 3, EWVIT_ERR_INVALID_ARG, "ewvit_conv1x1_gated_nhwc_bf16: act must be 0, 1 or 3");
+    EWVIT_REQUIRE(ewvit_aligned16(x) && ewvit_aligned16(gate) && ewvit_aligned16(w) && ewvit_aligned16(y) && ewvit_aligned16(residual),
+                  EWVIT_ERR_INVALID_ARG, "ewvit_conv1x1_gated_nhwc_bf16: pointers must be 16-byte aligned");
+    int rc = ewvit_check_device();
+    if (rc != EWVIT_OK) return rc;
+    const int bn = cout > 128 ? 256 : 128;
+    const long long rows = (long long)n * hw;
+    const int num_kb = (cin + BK - 1) / BK;
+    GemmParams p = {};
+    p.a_mode = A_SCALED;
+    p.a_ptr = static_cast<const __nv_bfloat16 *>(x);
+    p.a_gate = gate;
+    p.a_hw = hw;
+    p.a_k = cin;
+    p.N = cout;
+    p.M = rows;
+    p.tiles_m = (int)((rows + BM - 1) / BM);
+    p.tiles_n = (cout + bn - 1) / bn;
+    p.splits = 1;
+    p.chunks_per_tap = num_kb;
+    p.num_kb = num_kb;
+    p.kb_per_split = num_kb;
+    p.out = y; p.out_fp32 = 0; p.ldo = cout; p.col_off = 0;
+    p.shift = bias; p.act = act;
+    p.residual_bf16 = static_cast<const __nv_bfloat16 *>(residual);
+    p.ldr = cout;
+    p.stage_bytes = kTileBytes + bn * BK * 2;
+    p.stages = bn == 256 ? 4 : 6;
+    CUtensorMap tmA, tmB, tmC;
+    uint64_t dimsa[2] = {(uint64_t)cin, (uint64_t)rows}, dimsb[2] = {(uint64_t)cin, (uint64_t)cout}, str[2] = {2, (uint64_t)cin * 2};
+    uint32_t boxa[2] = {BK, BM}, boxb[2] = {BK, (uint32_t)bn};
+    rc = ewvit_make_tmap_bf16(&tmA, x, 2, dimsa, str, boxa, nullptr);
+    if (rc != EWVIT_OK) return rc;
+    rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, str, boxb, nullptr);
+    if (rc != EWVIT_OK) return rc;
+    rc = make_out_tmap(&tmC, y, true, rows, cout, 0, 0, 0);
+    if (rc != EWVIT_OK) return rc;
+    return launch_gemm(tmA, tmB, tmC, p, EPI_BB, (cudaStream_t)stream, bn);
 }

@@ -225,9 +225,11 @@ class NativeEffNetV2:
     scaling in one kernel; the stem reads the fp32 NCHW frames directly.  NHWC bf16 activations, BatchNorm folded."""
 
     def __init__(self, features: nn.Module, device):
+        import os
         dev = torch.device(device)
         self.device = dev
         self.ops = []
+        self.fuse_se = os.environ.get("EWVIT_SE_FUSED", "1") == "1"
         mods = list(features)
         stem = mods[0]
         w, b = _fold_conv_bn(stem[0], stem[1])
@@ -261,7 +263,9 @@ class NativeEffNetV2:
                                      se.fc2.weight.detach().float().flatten(1).t().contiguous().to(dev),
                                      se.fc2.bias.detach().float().to(dev)))
                     w2, b2 = _fold_conv_bn(pr[0], pr[1])
-                    self.ops.append(("conv1", w2.flatten(1).to(torch.bfloat16).to(dev).contiguous(), b2.to(dev), None, res, True))
+                    # project conv: the SE gate is applied while its A operand is assembled ("conv1g")
+                    self.ops.append(("conv1g" if self.fuse_se else "conv1", w2.flatten(1).to(torch.bfloat16).to(dev).contiguous(),
+                                     b2.to(dev), None, res, True))
                 else:
                     raise EwvitError(f"native backbone: unsupported block {kind}")
         head = mods[-1]
@@ -273,6 +277,7 @@ class NativeEffNetV2:
         block_in = None      # input of the current residual block
         x = None
         pooled = None
+        gate = None
         for i, op in enumerate(self.ops):
             kind = op[0]
             with stage(f"bb.{kind}" if TIMER is None or not getattr(TIMER, "per_layer", False) else f"bb.{i:03d}.{kind}"):
@@ -295,7 +300,15 @@ class NativeEffNetV2:
                     pooled = torch.empty((n, c), dtype=torch.float32, device=x.device)
                     x = ops.dwconv3x3(x, w, b, stride, pooled=pooled)
                 elif kind == "se":
-                    ops.se_apply(x, pooled, op[1], op[2], op[3], op[4])
+                    if self.fuse_se:
+                        gate = ops.se_gate(pooled, op[1], op[2], op[3], op[4])
+                    else:
+                        ops.se_apply(x, pooled, op[1], op[2], op[3], op[4])
+                elif kind == "conv1g":
+                    _, w, b, act, res, ends = op
+                    x = ops.conv1x1_gated(x, gate, w, bias=b, act=act, residual=block_in if res else None)
+                    if ends:
+                        block_in = x
         return x
 
 

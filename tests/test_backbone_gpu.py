@@ -99,6 +99,35 @@ def test_se_apply(ops):
     _close(xd.permute(0, 3, 1, 2), ref, tol=1e-3)
 
 
+@pytest.mark.parametrize("c,cout,hw,res", [(960, 160, (14, 14), True), (1536, 256, (7, 7), True), (256, 128, (14, 14), False),
+                                           (768, 160, (14, 14), False)])
+def test_gated_project_conv(ops, c, cout, hw, res):
+    """SE gate fused into the project conv's A path == scale pass followed by the plain 1x1 conv."""
+    n, (h, w) = 5, hw
+    x = seeded_randn((n, c, h, w), 21).bfloat16()
+    gate = torch.sigmoid(seeded_randn((n, c), 22))
+    wt = (seeded_randn((cout, c, 1, 1), 23) * c ** -0.5).bfloat16()
+    b = seeded_randn((cout,), 24)
+    r = seeded_randn((n, cout, h, w), 25).bfloat16() if res else None
+    xs = (x.float() * gate.view(n, c, 1, 1)).bfloat16().float()      # the kernel rounds the scaled operand to bf16
+    ref = F.conv2d(xs, wt.float(), b)
+    if res:
+        ref = ref + r.float()
+    got = ops.conv1x1_gated(_nhwc(x).cuda(), gate.cuda().contiguous(), wt.flatten(1).contiguous().cuda(), bias=b.cuda(),
+                            residual=_nhwc(r).cuda() if res else None)
+    _close(got.permute(0, 3, 1, 2), ref)
+
+
+def test_se_gate(ops):
+    n, c, sq = 6, 960, 40
+    pooled = seeded_randn((n, c), 26)
+    w1, b1 = seeded_randn((sq, c), 27) * c ** -0.5, seeded_randn((sq,), 28)
+    w2, b2 = seeded_randn((c, sq), 29) * sq ** -0.5, seeded_randn((c,), 30)
+    ref = torch.sigmoid(F.silu(pooled @ w1.t() + b1) @ w2.t() + b2)
+    got = ops.se_gate(pooled.cuda(), w1.cuda(), b1.cuda(), w2.t().contiguous().cuda(), b2.cuda())
+    _close(got, ref, tol=1e-3, bf16_out=False)
+
+
 def test_native_backbone_matches_torchvision(dama_sd, golden):
     from ewvit import engine
     from oracle import ewvit_oracle as O
