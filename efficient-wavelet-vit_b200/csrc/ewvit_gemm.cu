@@ -28,18 +28,29 @@ constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int kStages = 6;
 constexpr int kAccStages = 2;
 constexpr int kTileBytes = BM * BK * 2;        // 16 KiB
-constexpr int kEpiWarps = 8;                   // 2 warps per TMEM lane quarter, each takes half the columns
-constexpr int kThreads = 64 + 32 * kEpiWarps;  // 320
 enum { EPI_CONV = 0, EPI_LINEAR = 1, EPI_PARTIAL = 2, EPI_BB = 3 };
-constexpr int kBuilderWarps = 8;                // A_IM2COL only: 256 threads assemble the A tiles in shared memory
+constexpr int kBuilderWarps = 8;                // A_IM2COL / A_SCALED only: 256 threads assemble or rescale the A tiles in shared memory
 constexpr int kBuilderSlots = 4;                // ring slots are owned by builder-warp PAIRS (64 rows each)
-constexpr int kThreadsBuilder = kThreads + 32 * kBuilderWarps;   // 576
 constexpr int kMaxHalo = 8;                     // A_IM2COL: halo ring depth (TMA latency of the small-row boxes is ~3 us)
 constexpr int kStgBytes = 32 * 64;               // one epilogue chunk: 32 rows x 32 bf16, dense, 64B-swizzled (TMA store box)
-constexpr int kStagingBytes = kEpiWarps * kStgBytes;   // 16 KiB: per-warp staging buffers of the epilogue
-constexpr int kOperandBytes = 200 * 1024;       // operand stages (+ halo buffers)
-constexpr int kPayloadBytes = kOperandBytes + kStagingBytes;   // barriers live right behind       // operand stages (+ halo buffers); barriers live right behind
-constexpr int kSmemBytes = kPayloadBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+// Epilogue warps come in groups of four (one warp per TMEM lane quarter).  Kernels without builder warps run FOUR
+// groups: two per accumulator stage, each draining half of the tile's columns -- short-K layers are bound by the
+// epilogue's latency chain (tcgen05.ld -> MUFU -> staging -> TMA store, ~1200 cycles per 32x32 chunk with two warps per
+// scheduler), and twice the warps hide twice the latency.  Only the backbone's plain 1x1 convs (EPI_BB without
+// builders: K <= 256) do this: their operand ring can be shallow, which pays for the second set of staging buffers.
+// Builder kernels keep two groups (register file); the long-K MWT convs and the linears keep the deep ring.
+template <int kEpi, bool kBuilder>
+struct Cfg {
+    static constexpr bool kWideEpi = kEpi == EPI_BB && !kBuilder;
+    static constexpr int kEpiWarps = kWideEpi ? 16 : 8;
+    static constexpr int kEpiGroups = kEpiWarps / 4;
+    static constexpr int kHalves = kEpiGroups / 2;                       // column halves per accumulator stage
+    static constexpr int kThreads = 64 + 32 * kEpiWarps + (kBuilder ? 32 * kBuilderWarps : 0);
+    static constexpr int kStagingBytes = kEpiWarps * kStgBytes;          // per-warp staging buffers of the epilogue
+    static constexpr int kOperandBytes = (kWideEpi ? 160 : 200) * 1024;  // operand stages (+ halo buffers)
+    static constexpr int kPayloadBytes = kOperandBytes + kStagingBytes;  // barriers live right behind
+    static constexpr int kSmemBytes = kPayloadBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+};
 
 enum { A_FLAT = 0, A_TILE4D = 1, A_IM2COL = 2, A_SCALED = 3 };
 
@@ -135,12 +146,14 @@ __device__ __forceinline__ void tma_store_4d(const void *tmap, uint32_t src, int
     } while (0)
 
 template <int kEpi, bool kBuilder, int kBN>
-__global__ void __launch_bounds__(kBuilder ? kThreadsBuilder : kThreads, 1)
+__global__ void __launch_bounds__(Cfg<kEpi, kBuilder>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + kPayloadBytes);
+    constexpr int kEpiWarps = Cfg<kEpi, kBuilder>::kEpiWarps, kHalves = Cfg<kEpi, kBuilder>::kHalves;
+    constexpr int kOperandBytes = Cfg<kEpi, kBuilder>::kOperandBytes;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + Cfg<kEpi, kBuilder>::kPayloadBytes);
     unsigned long long *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages,
                        *tempty = bars + 2 * kStages + kAccStages;
     unsigned long long *hfull = bars + 2 * kStages + 2 * kAccStages, *hempty = hfull + kMaxHalo;
@@ -161,7 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ewvit::tma_prefetch_desc(&tmA);
         ewvit::tma_prefetch_desc(&tmB);
         for (int s = 0; s < kStages; ++s) {
-            ewvit::mbar_init(ewvit::smem_u32(&full[s]), !kBuilder ? 1 : p.a_mode == A_SCALED ? kBuilderWarps : (p.b_res ? 2 : 3));   // [TMA B] + two builder halves | all builder warps
+            ewvit::mbar_init(ewvit::smem_u32(&full[s]), !kBuilder ? 1 : p.a_mode == A_SCALED ? 2 : (p.b_res ? 2 : 3));   // [TMA B] + the two warps of the slot's builder pair
             ewvit::mbar_init(ewvit::smem_u32(&empty[s]), 1);
         }
         for (int a = 0; a < kAccStages; ++a) {
@@ -327,9 +340,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // `raw` barrier (the halo barriers, unused in this mode); the 256 builder threads multiply the tile by the
             // squeeze-excitation gate IN PLACE (swizzled 16-byte chunks, 4 rows per thread) and only then hand the slot
             // to the tensor core.  Global traffic stays asynchronous and the separate x *= gate pass is gone.
-            const int j = btid & 7;                 // 16-byte chunk (8 channels) of the 64-channel k-block
-            const int rbase = btid >> 3;            // rows rbase + 32 i, i = 0..3  (all have the same swizzle phase)
-            const uint32_t chunk_off = (uint32_t)rbase * 128u + (((uint32_t)j ^ (uint32_t)(rbase & 7)) << 4);
+            // Ring slots are owned by builder-warp PAIRS (slot & 3 == pair), so up to four k-blocks are rescaled
+            // concurrently and the gate loads / fence of one overlap the copies of the others.
+            const int pair = bwarp & (kBuilderSlots - 1);
+            const int t64 = (bwarp >> 2) * 32 + lane;   // thread within the pair
+            const int j = t64 & 7;                      // 16-byte chunk (8 channels) of the 64-channel k-block
+            const int rb = t64 >> 3;                    // rows rb + 8 i, i = 0..15  (all have the same swizzle phase rb)
+            const uint32_t chunk_off = (uint32_t)rb * 128u + (((uint32_t)j ^ (uint32_t)rb) << 4);
             const int last_frame = (int)((p.M - 1) / p.a_hw);
             uint32_t g = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -337,46 +354,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int sp = (w / p.tiles_m) / p.tiles_n;
                 const int kb0 = sp * p.kb_per_split;
                 const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
-                const float *gp[4];
+                // gate row (frame) of each of this thread's 16 tile rows; rows past M are zero-filled by TMA
+                int goff[16];
+                {
+                    const long long row0 = (long long)m_t * BM + rb;
+                    int fr = (int)(row0 / p.a_hw);
+                    int rem = (int)(row0 - (long long)fr * p.a_hw);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const long long row = (long long)m_t * BM + rbase + 32 * i;
-                    const int fr = min((int)(row / p.a_hw), last_frame);     // rows past M are zero-filled by TMA
-                    gp[i] = p.a_gate + (long long)fr * p.a_k + j * 8;
+                    for (int i = 0; i < 16; ++i) {
+                        goff[i] = min(fr, last_frame) * p.a_k + j * 8;
+                        rem += 8;
+                        while (rem >= p.a_hw) { rem -= p.a_hw; ++fr; }
+                    }
                 }
                 for (int kb = kb0; kb < kb1; ++kb, ++g) {
                     const int stage = (int)(g % (uint32_t)nstages);
+                    if ((stage & (kBuilderSlots - 1)) != pair) continue;
                     const uint32_t phase = (g / (uint32_t)nstages) & 1u;
                     const bool kin = kb * BK + j * 8 < p.a_k;               // K tail: the tile holds zeros there
-                    float4 g0[4], g1[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        g0[i] = g1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (kin) {
-                            g0[i] = __ldg(reinterpret_cast<const float4 *>(gp[i] + kb * BK));
-                            g1[i] = __ldg(reinterpret_cast<const float4 *>(gp[i] + kb * BK) + 1);
-                        }
-                    }
-                    ewvit::mbar_wait(ewvit::smem_u32(&hfull[stage]), phase);
+                    const float *gk = p.a_gate + kb * BK;
                     const uint32_t a_base = smem_base + stage * kStageB + chunk_off;
-                    uint4 v[4];
+                    bool waited = false;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
-                                     : "r"(a_base + i * 32 * 128) : "memory");
+                    for (int b4 = 0; b4 < 4; ++b4) {
+                        float4 g0[4], g1[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const __nv_bfloat162 *vp = reinterpret_cast<const __nv_bfloat162 *>(&v[i]);
-                        const float2 f0 = __bfloat1622float2(vp[0]), f1 = __bfloat1622float2(vp[1]);
-                        const float2 f2 = __bfloat1622float2(vp[2]), f3 = __bfloat1622float2(vp[3]);
-                        const __nv_bfloat162 o0 = __floats2bfloat162_rn(f0.x * g0[i].x, f0.y * g0[i].y);
-                        const __nv_bfloat162 o1 = __floats2bfloat162_rn(f1.x * g0[i].z, f1.y * g0[i].w);
-                        const __nv_bfloat162 o2 = __floats2bfloat162_rn(f2.x * g1[i].x, f2.y * g1[i].y);
-                        const __nv_bfloat162 o3 = __floats2bfloat162_rn(f3.x * g1[i].z, f3.y * g1[i].w);
-                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + i * 32 * 128),
-                                     "r"(*reinterpret_cast<const uint32_t *>(&o0)), "r"(*reinterpret_cast<const uint32_t *>(&o1)),
-                                     "r"(*reinterpret_cast<const uint32_t *>(&o2)), "r"(*reinterpret_cast<const uint32_t *>(&o3))
-                                     : "memory");
+                        for (int i = 0; i < 4; ++i) {
+                            g0[i] = g1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (kin) {
+                                g0[i] = __ldg(reinterpret_cast<const float4 *>(gk + goff[b4 * 4 + i]));
+                                g1[i] = __ldg(reinterpret_cast<const float4 *>(gk + goff[b4 * 4 + i]) + 1);
+                            }
+                        }
+                        if (!waited) {
+                            ewvit::mbar_wait(ewvit::smem_u32(&hfull[stage]), phase);
+                            waited = true;
+                        }
+                        uint4 v[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
+                                         : "r"(a_base + (b4 * 4 + i) * 1024) : "memory");
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const __nv_bfloat162 *vp = reinterpret_cast<const __nv_bfloat162 *>(&v[i]);
+                            const float2 f0 = __bfloat1622float2(vp[0]), f1 = __bfloat1622float2(vp[1]);
+                            const float2 f2 = __bfloat1622float2(vp[2]), f3 = __bfloat1622float2(vp[3]);
+                            const __nv_bfloat162 o0 = __floats2bfloat162_rn(f0.x * g0[i].x, f0.y * g0[i].y);
+                            const __nv_bfloat162 o1 = __floats2bfloat162_rn(f1.x * g0[i].z, f1.y * g0[i].w);
+                            const __nv_bfloat162 o2 = __floats2bfloat162_rn(f2.x * g1[i].x, f2.y * g1[i].y);
+                            const __nv_bfloat162 o3 = __floats2bfloat162_rn(f3.x * g1[i].z, f3.y * g1[i].w);
+                            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + (b4 * 4 + i) * 1024),
+                                         "r"(*reinterpret_cast<const uint32_t *>(&o0)), "r"(*reinterpret_cast<const uint32_t *>(&o1)),
+                                         "r"(*reinterpret_cast<const uint32_t *>(&o2)), "r"(*reinterpret_cast<const uint32_t *>(&o3))
+                                         : "memory");
+                        }
                     }
                     ewvit::fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
                     __syncwarp();
@@ -485,18 +517,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ---------------------------------------------------------------- epilogue (warps 2..9)
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int grp = (warp - 2) >> 2;        // two groups of 4 warps: group g drains accumulator stage g, i.e. every
-                                                // other tile of this CTA, so two tiles are in flight in the epilogue
+        const int grp = (warp - 2) >> 2;        // groups of 4 warps: group g drains accumulator stage g & 1, i.e. every
+                                                // other tile of this CTA (two tiles in flight in the epilogue), and with
+                                                // four groups only column half g >> 1 of it
+        const int half = grp >> 1;
         const int r = q * 32 + lane;            // row of the tile owned by this thread
         const int gtid = (threadIdx.x - 64) & 127;
-        float *g_scale = s_scale + grp * kBN, *g_shift = s_shift + grp * kBN;
+        const int acc = grp & 1;
+        float *g_scale = s_scale + acc * kBN, *g_shift = s_shift + acc * kBN;
+        constexpr int kColsPerGroup = kBN / kHalves;
         const uint32_t stg = smem_base + kOperandBytes + (uint32_t)(warp - 2) * kStgBytes;
-        const int acc = grp;
         uint32_t acc_phase = 0;
         int cur_nt = -1;
         int it = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
-            if ((it & 1) != grp) continue;
+            if ((it & 1) != acc) continue;
             if (q == 2 && lane == 0) EWVIT_TRACE(2 + grp, it, 0);
             const int m_t = w % p.tiles_m;
             const int wn = w / p.tiles_m;
@@ -505,7 +540,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
             if ((kEpi == EPI_CONV || kEpi == EPI_BB) && n_t != cur_nt) {   // (re)stage the per-channel scale/shift of this column tile
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-                for (int i = gtid; i < kBN; i += 128) {
+                for (int i = half * kColsPerGroup + gtid; i < (half + 1) * kColsPerGroup; i += 128) {
                     const bool in = n_t * kBN + i < p.N;
                     g_scale[i] = (p.scale && in) ? p.scale[n_t * kBN + i] : 1.f;
                     g_shift[i] = (p.shift && in) ? p.shift[n_t * kBN + i] : 0.f;
@@ -548,10 +583,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (q == 2 && lane == 0) EWVIT_TRACE(2 + grp, it, 1);
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kBN);
 #pragma unroll 1
-            for (int c = 0; c < kBN / 32; ++c) {
+            for (int c = half * (kColsPerGroup / 32); c < (half + 1) * (kColsPerGroup / 32); ++c) {
                 if (kEpi == EPI_BB && n_t * kBN + c * 32 >= p.N) continue;   // warp-uniform: nothing valid in this chunk
                 uint32_t v[32];
                 ewvit::tmem_ld_32x32(t_row + c * 32, v);
+                // skip-connection values of the whole chunk are requested before the accumulator wait (row-per-lane 16-byte
+                // loads: as four dependent L2 round trips they made the residual layers' epilogue ~2900 cycles per chunk)
+                uint4 rcur[4];
+                if (kEpi == EPI_BB && p.residual_bf16) {
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        const int col = n_t * kBN + c * 32 + g8 * 8;
+                        rcur[g8] = make_uint4(0u, 0u, 0u, 0u);
+                        if (valid && col < p.N) rcur[g8] = __ldg(reinterpret_cast<const uint4 *>(p.residual_bf16 + orow * p.ldr + col));
+                    }
+                }
                 ewvit::tmem_ld_wait();
                 const int col0 = n_t * kBN + c * 32;
                 if (kEpi == EPI_BB) {
@@ -570,9 +616,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int i = 0; i < 8; ++i) f8[i] = fmaxf(f8[i], 0.f);
                         }
-                        if (p.residual_bf16 && valid && col < p.N) {   // skip connection is added AFTER the activation
-                            const uint4 rv = *reinterpret_cast<const uint4 *>(p.residual_bf16 + orow * p.ldr + col);
-                            const __nv_bfloat162 *rp = reinterpret_cast<const __nv_bfloat162 *>(&rv);
+                        if (p.residual_bf16) {   // skip connection is added AFTER the activation (zeros past N / past M)
+                            const __nv_bfloat162 *rp = reinterpret_cast<const __nv_bfloat162 *>(&rcur[g8]);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const float2 r2 = __bfloat1622float2(rp[i]);
@@ -726,18 +771,21 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
     int dev = 0;
     EWVIT_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        EWVIT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kBuilder, kBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kBuilder, kBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kEpi, kBuilder>::kSmemBytes));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     if (p.stage_bytes <= 0) p.stage_bytes = kTileBytes + kBN * BK * 2;
-    if (p.stages <= 0) p.stages = kBN == 128 ? kStages : kOperandBytes / (kTileBytes + kBN * BK * 2);
+    if (p.stages <= 0) {
+        p.stages = Cfg<kEpi, kBuilder>::kOperandBytes / (kTileBytes + kBN * BK * 2);
+        if (p.stages > kStages) p.stages = kStages;
+    }
     p.trace = g_trace;
     p.dbg = g_dbg;
     long long work = (long long)p.tiles_m * p.tiles_n * p.splits;
     long long grid = ewvit_num_sms();
     if (grid > work) grid = work;
     if (grid <= 0) return EWVIT_OK;
-    gemm_tc_kernel<kEpi, kBuilder, kBN><<<(unsigned)grid, kBuilder ? kThreadsBuilder : kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+    gemm_tc_kernel<kEpi, kBuilder, kBN><<<(unsigned)grid, Cfg<kEpi, kBuilder>::kThreads, Cfg<kEpi, kBuilder>::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }
@@ -1054,8 +1102,8 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
             }
             p.stage_bytes = sbytes;
             p.stages = bn == 256 ? 3 : 4;
-            while (p.stages > 2 && (kOperandBytes - reserve - p.stages * sbytes) / p.halo_stride < 2) p.stages -= 1;
-            p.halo_bufs = (kOperandBytes - reserve - p.stages * sbytes) / p.halo_stride;
+            while (p.stages > 2 && (Cfg<EPI_BB, true>::kOperandBytes - reserve - p.stages * sbytes) / p.halo_stride < 2) p.stages -= 1;
+            p.halo_bufs = (Cfg<EPI_BB, true>::kOperandBytes - reserve - p.stages * sbytes) / p.halo_stride;
             if (p.halo_bufs > kMaxHalo) p.halo_bufs = kMaxHalo;
             EWVIT_REQUIRE(p.halo_bufs >= 2, EWVIT_ERR_UNSUPPORTED, "ewvit_conv_nhwc_bf16: halo too large");
             p.bres_off = p.stages * sbytes + p.halo_bufs * p.halo_stride;
