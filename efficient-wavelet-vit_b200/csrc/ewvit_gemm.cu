@@ -32,6 +32,8 @@ enum { EPI_CONV = 0, EPI_LINEAR = 1, EPI_PARTIAL = 2, EPI_BB = 3 };
 constexpr int kBuilderWarps = 8;                // A_IM2COL / A_SCALED only: 256 threads assemble or rescale the A tiles in shared memory
 constexpr int kBuilderSlots = 4;                // ring slots are owned by builder-warp PAIRS (64 rows each)
 constexpr int kMaxHalo = 8;                     // A_IM2COL: halo ring depth (TMA latency of the small-row boxes is ~3 us)
+constexpr int kFlat3Rows = BM + 8;               // 136 rows = 17 swizzle atoms: rows [m0 - 1, m0 + 135) cover the shifts 0..2
+constexpr int kFlat3ABytes = kFlat3Rows * BK * 2; // 17408
 constexpr int kStgBytes = 32 * 64;               // one epilogue chunk: 32 rows x 32 bf16, dense, 64B-swizzled (TMA store box)
 // Epilogue warps come in groups of four (one warp per TMEM lane quarter).  Kernels without builder warps run FOUR
 // groups: two per accumulator stage, each draining half of the tile's columns -- short-K layers are bound by the
@@ -95,6 +97,10 @@ struct GemmParams {
     const float *a_gate;   // [frames, K] fp32
     int a_hw;              // rows (pixels) per frame
     int a_k;               // K = row pitch of A and of the gate
+    int flat3;           // A_FLAT 3x3 conv, "row-shared" taps: one ring slot = (dy, channel chunk) holds ONE window of
+                         // kFlat3Rows activation rows and the three weight tiles of dx = 0,1,2; the three A operands are the
+                         // same window read at a start address shifted by 0/1/2 rows, so every activation row crosses
+                         // L2 -> shared memory 3 times per tile instead of 9
     int stage_bytes;     // ring slot size: A tile (+ B tile unless the weights are resident)
     int b_res;           // A_IM2COL: all k-blocks of B stay resident in shared memory (loaded once per CTA)
     int bres_off;        // byte offset of the resident B region
@@ -209,11 +215,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0, hb = 0;
         uint32_t phase = 0, hphase = 0;
         int tt = 0;
-        if (kBuilder && p.b_res) {     // weights are tiny and identical for every tile: fetch all k-blocks once
+        if ((kBuilder || p.flat3) && p.b_res) {     // weights are small and identical for every tile: fetch all k-blocks once
+            const int nb = p.flat3 ? 3 * p.num_kb : p.num_kb;    // flat3: num_kb counts (dy, chunk) slots of three taps each
             if (ewvit::elect_one()) {
                 const uint32_t bb = ewvit::smem_u32(bres_bar);
-                ewvit::mbar_expect_tx(bb, (uint32_t)(p.num_kb * kBTileB));
-                for (int kb = 0; kb < p.num_kb; ++kb)
+                ewvit::mbar_expect_tx(bb, (uint32_t)(nb * kBTileB));
+                for (int kb = 0; kb < nb; ++kb)
                     ewvit::tma_load_2d(smem_base + p.bres_off + kb * kBTileB, &tmB, kb * BK, 0, bb);
             }
             __syncwarp();
@@ -262,6 +269,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             int tap = kb0 / p.chunks_per_tap, chunk = kb0 - tap * p.chunks_per_tap;
             const int ax0 = tx * p.box_w * p.in_stride, ay0 = ty * p.box_h * p.in_stride;
+            if (p.flat3) {
+                for (int kb = kb0; kb < kb1; ++kb) {       // kb = dy * chunks + chunk
+                    const int dy = kb / p.chunks_per_tap, ch = kb - dy * p.chunks_per_tap;
+                    ewvit::mbar_wait(ewvit::smem_u32(&empty[stage]), phase ^ 1);
+                    const uint32_t bar = ewvit::smem_u32(&full[stage]);
+                    const uint32_t a_dst = smem_base + stage * kStageB;
+                    if (ewvit::elect_one()) {
+                        ewvit::mbar_expect_tx(bar, kStageB);
+                        ewvit::tma_load_2d(a_dst, &tmA, ch * BK, m_t * BM + p.tap_a0[dy * 3], bar);
+                        if (!p.b_res) {
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx)
+                                ewvit::tma_load_2d(a_dst + kFlat3ABytes + dx * kBTileB, &tmB, ((dy * 3 + dx) * p.chunks_per_tap + ch) * BK, n_t * kBN, bar);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+                if (lane == 0) EWVIT_TRACE(0, tt, 1);
+                continue;
+            }
             for (int kb = kb0; kb < kb1; ++kb) {
                 ewvit::mbar_wait(ewvit::smem_u32(&empty[stage]), phase ^ 1);
                 // A_SCALED: the builders post-process the raw tile, so completion goes to the `raw` (halo) barrier
@@ -288,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int acc = 0;
         uint32_t acc_phase = 0;
         int tt = 0;
-        if (kBuilder && p.b_res) ewvit::mbar_wait(ewvit::smem_u32(bres_bar), 0);
+        if ((kBuilder || p.flat3) && p.b_res) ewvit::mbar_wait(ewvit::smem_u32(bres_bar), 0);
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tt) {
             if (lane == 0) EWVIT_TRACE(1, tt, 0);
             const int wn = w / p.tiles_m;
@@ -311,7 +339,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint64_t b_desc = ewvit::umma_desc_sw128((kBuilder && p.b_res) ? smem_base + p.bres_off + kb * kBTileB : a_addr + kTileBytes);
                 const uint32_t ebar = ewvit::smem_u32(&empty[stage]);
                 const uint32_t first = kb > kb0 ? 1u : 0u;
-                if (ewvit::elect_one()) {
+                if (p.flat3) {
+                    if (ewvit::elect_one()) {
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            // the operand of tap dx is the window shifted by dx rows (128 bytes): the 128B swizzle is a function
+                            // of the shared-memory address, so a row-shifted start address reads what TMA wrote for row r + dx
+                            // (verified on hardware; the descriptor's base-offset field must stay 0 for this)
+                            const uint64_t ad = ewvit::umma_desc_sw128(a_addr + dx * 128);
+                            const int dy = kb / p.chunks_per_tap, ch = kb - dy * p.chunks_per_tap;
+                            const uint64_t bd = ewvit::umma_desc_sw128(
+                                p.b_res ? smem_base + p.bres_off + ((dy * 3 + dx) * p.chunks_per_tap + ch) * kBTileB : a_addr + kFlat3ABytes + dx * kBTileB);
+                            ewvit::umma_bf16(d_tmem, ad, bd, idesc, (dx > 0 || kb > kb0) ? 1u : 0u);
+                            ewvit::umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                            ewvit::umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                            ewvit::umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                        }
+                        ewvit::umma_commit(ebar);
+                    }
+                } else if (ewvit::elect_one()) {
                     // advancing 16 K-elements = 32 bytes = +2 in the descriptor's (address >> 4) field
                     ewvit::umma_bf16(d_tmem, a_desc, b_desc, idesc, first);
                     ewvit::umma_bf16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
@@ -973,6 +1019,25 @@ extern "C" int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, in
         p.tiles_m = (int)((rows + BM - 1) / BM);
         for (int dy = 0; dy < 3; ++dy)
             for (int dx = 0; dx < 3; ++dx) p.tap_a0[dy * 3 + dx] = (dy - 1) * win + (dx - 1);
+        if (!(g_dbg & 32)) {      // row-shared taps (debug flag 32 = the one-tile-per-tap path)
+            box[1] = kFlat3Rows;
+            rc = ewvit_make_tmap_bf16(&tmA, x, 2, dims, str, box, nullptr);
+            if (rc != EWVIT_OK) return rc;
+            p.flat3 = 1;
+            p.num_kb = 3 * chunks;
+            p.kb_per_split = p.num_kb;
+            p.stage_bytes = kFlat3ABytes + 3 * BN * BK * 2;
+            p.stages = Cfg<EPI_CONV, false>::kOperandBytes / p.stage_bytes;
+            // small filter banks (the 64 -> 128 fusion conv: 144 KB) stay resident; the ring then carries activation windows only
+            const int wbytes = 9 * cin * BN * 2;
+            if (p.tiles_n == 1 && !(g_dbg & 64) && wbytes + 3 * kFlat3ABytes <= Cfg<EPI_CONV, false>::kOperandBytes) {
+                p.b_res = 1;
+                p.stage_bytes = kFlat3ABytes;
+                p.stages = (Cfg<EPI_CONV, false>::kOperandBytes - wbytes) / kFlat3ABytes;
+                if (p.stages > kStages) p.stages = kStages;
+                p.bres_off = p.stages * kFlat3ABytes;
+            }
+        }
         p.pad_hp = hin;
         p.pad_wp = win;
     } else {
