@@ -25,7 +25,7 @@
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kStages = 6;
+constexpr int kStages = 12;          // barrier slots; the ring depth actually used is GemmParams::stages
 constexpr int kAccStages = 2;
 constexpr int kTileBytes = BM * BK * 2;        // 16 KiB
 enum { EPI_CONV = 0, EPI_LINEAR = 1, EPI_PARTIAL = 2, EPI_BB = 3 };
@@ -215,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0, hb = 0;
         uint32_t phase = 0, hphase = 0;
         int tt = 0;
-        if ((kBuilder || p.flat3) && p.b_res) {     // weights are small and identical for every tile: fetch all k-blocks once
+        if (p.b_res) {     // weights are small and identical for every tile: fetch all k-blocks once
             const int nb = p.flat3 ? 3 * p.num_kb : p.num_kb;    // flat3: num_kb counts (dy, chunk) slots of three taps each
             if (ewvit::elect_one()) {
                 const uint32_t bb = ewvit::smem_u32(bres_bar);
@@ -301,7 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         ewvit::tma_load_2d(a_dst, &tmA, chunk * BK, m_t * BM + p.tap_a0[tap], bar);
                     else
                         ewvit::tma_load_4d(a_dst, &tmA, chunk * BK, ax0 + p.tap_a0[tap], ay0 + p.tap_a1[tap], img, bar);
-                    ewvit::tma_load_2d(a_dst + kTileBytes, &tmB, kb * BK, n_t * kBN, bar);
+                    if (!p.b_res) ewvit::tma_load_2d(a_dst + kTileBytes, &tmB, kb * BK, n_t * kBN, bar);
                 }
                 __syncwarp();
                 if (++chunk == p.chunks_per_tap) { chunk = 0; ++tap; }
@@ -316,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int acc = 0;
         uint32_t acc_phase = 0;
         int tt = 0;
-        if ((kBuilder || p.flat3) && p.b_res) ewvit::mbar_wait(ewvit::smem_u32(bres_bar), 0);
+        if (p.b_res) ewvit::mbar_wait(ewvit::smem_u32(bres_bar), 0);
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tt) {
             if (lane == 0) EWVIT_TRACE(1, tt, 0);
             const int wn = w / p.tiles_m;
@@ -336,7 +336,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ewvit::tc_fence_after();
                 const uint32_t a_addr = smem_base + stage * kStageB;
                 const uint64_t a_desc = ewvit::umma_desc_sw128(a_addr);
-                const uint64_t b_desc = ewvit::umma_desc_sw128((kBuilder && p.b_res) ? smem_base + p.bres_off + kb * kBTileB : a_addr + kTileBytes);
+                const uint64_t b_desc = ewvit::umma_desc_sw128(p.b_res ? smem_base + p.bres_off + kb * kBTileB : a_addr + kTileBytes);
                 const uint32_t ebar = ewvit::smem_u32(&empty[stage]);
                 const uint32_t first = kb > kb0 ? 1u : 0u;
                 if (p.flat3) {
@@ -630,7 +630,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kBN);
 #pragma unroll 1
             for (int c = half * (kColsPerGroup / 32); c < (half + 1) * (kColsPerGroup / 32); ++c) {
-                if (kEpi == EPI_BB && n_t * kBN + c * 32 >= p.N) continue;   // warp-uniform: nothing valid in this chunk
+                if ((kEpi == EPI_BB || kEpi == EPI_CONV) && n_t * kBN + c * 32 >= p.N) continue;   // warp-uniform: nothing valid in this chunk
                 uint32_t v[32];
                 ewvit::tmem_ld_32x32(t_row + c * 32, v);
                 // skip-connection values of the whole chunk are requested before the accumulator wait (row-per-lane 16-byte
@@ -823,7 +823,18 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
     if (p.stage_bytes <= 0) p.stage_bytes = kTileBytes + kBN * BK * 2;
     if (p.stages <= 0) {
         p.stages = Cfg<kEpi, kBuilder>::kOperandBytes / (kTileBytes + kBN * BK * 2);
+        if (p.stages > 6) p.stages = 6;
+    }
+    // plain (one-tap-per-slot) paths with a single column tile and a small weight matrix: keep all of B resident and let
+    // the ring carry activation tiles only -- TMA's ~1.5 us latency makes throughput = bytes in flight / latency, and a
+    // slot without its B tile is half the size
+    if (!kBuilder && !p.flat3 && !p.b_res && p.tiles_n == 1 && p.splits == 1 && !(g_dbg & 64) &&
+        p.num_kb * kBN * BK * 2 <= 96 * 1024 && p.stage_bytes == kTileBytes + kBN * BK * 2) {
+        p.b_res = 1;
+        p.stage_bytes = kTileBytes;
+        p.stages = (Cfg<kEpi, kBuilder>::kOperandBytes - p.num_kb * kBN * BK * 2) / kTileBytes;
         if (p.stages > kStages) p.stages = kStages;
+        p.bres_off = p.stages * kTileBytes;
     }
     p.trace = g_trace;
     p.dbg = g_dbg;
@@ -1200,6 +1211,57 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
         rc = make_out_tmap(&tmC, y, false, 0, cout, n, ho, wo);
     if (rc != EWVIT_OK) return rc;
     return launch_gemm(tmA, tmB, tmC, p, EPI_BB, (cudaStream_t)stream, bn);
+}
+
+// Tensor-core head of one wavelet level, step 2 (mwt.py:84-86): the three per-colour Conv2d(3->18, 3x3, p1)+BN+ReLU as
+// ONE block-diagonal 9(16) -> 54(64) conv.  The input is the padded-flat [n, h+2, wd+2, 16] bf16 tensor of
+// ewvit_mwt_upsample_fwd.  With 16 channels per pixel, the three horizontal taps of an output pixel are 48 CONTIGUOUS
+// elements of that tensor, so the im2col row of a vertical tap dy is an overlapping window: the A operand comes from a
+// tensor map whose rows are 48 elements long but only 16 elements (one pixel) apart, fetched as 64-wide boxes whose last
+// 16 columns lie outside the map and are zero-filled.  K = 3 x 64, no im2col buffer, no builder warps.
+//   w [64, 192] bf16: w[g*18+oc][dy*64 + dx*16 + g*3+ic] = seperate[g].weight[oc][ic][dy][dx], zero elsewhere
+//   scale/shift [64] fp32 (folded BN, zeros past 54);  y [n, h+2, wd+2, 64] bf16 padded-flat (border written as zeros)
+extern "C" int ewvit_mwt_head_conv_fwd(const void *up, const void *w, int n, int h, int wd, const float *scale, const float *shift,
+                                       void *y, void *stream) {
+    EWVIT_REQUIRE(n >= 0 && h > 0 && wd > 0, EWVIT_ERR_INVALID_ARG, "ewvit_mwt_head_conv_fwd: bad sizes");
+    if (n == 0) return EWVIT_OK;
+    EWVIT_REQUIRE(up && w && scale && shift && y, EWVIT_ERR_INVALID_ARG, "ewvit_mwt_head_conv_fwd: NULL pointer");
+    EWVIT_REQUIRE(ewvit_aligned16(up) && ewvit_aligned16(w) && ewvit_aligned16(y), EWVIT_ERR_INVALID_ARG,
+                  "ewvit_mwt_head_conv_fwd: pointers must be 16-byte aligned");
+    int rc = ewvit_check_device();
+    if (rc != EWVIT_OK) return rc;
+    const int hin = h + 2, win = wd + 2, cpx = 16, cout = 64;
+    const long long rows = (long long)n * hin * win;
+    GemmParams p = {};
+    p.a_mode = A_FLAT;
+    p.chunks_per_tap = 1;
+    p.num_kb = 3;
+    p.kb_per_split = 3;
+    p.splits = 1;
+    p.N = cout;
+    p.tiles_n = 1;
+    p.M = rows;
+    p.tiles_m = (int)((rows + BM - 1) / BM);
+    for (int dy = 0; dy < 3; ++dy) p.tap_a0[dy] = (dy - 1) * win - 1;     // window starts at the left neighbour
+    p.pad_hp = hin;
+    p.pad_wp = win;
+    p.out = y; p.out_fp32 = 0; p.ldo = cout; p.col_off = 0;
+    p.scale = scale; p.shift = shift; p.act = 1;
+    CUtensorMap tmA, tmB, tmC;
+    {
+        // overlapping rows: row i = elements [16 i, 16 i + 48) of the flat tensor
+        uint64_t dims[2] = {(uint64_t)3 * cpx, (uint64_t)(rows - 2)}, str[2] = {2, (uint64_t)cpx * 2};
+        uint32_t box[2] = {BK, BM};
+        rc = ewvit_make_tmap_bf16(&tmA, up, 2, dims, str, box, nullptr);
+        if (rc != EWVIT_OK) return rc;
+        uint64_t dimsb[2] = {(uint64_t)3 * BK, (uint64_t)cout}, strb[2] = {2, (uint64_t)3 * BK * 2};
+        uint32_t boxb[2] = {BK, BN};
+        rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, strb, boxb, nullptr);
+        if (rc != EWVIT_OK) return rc;
+    }
+    rc = make_out_tmap(&tmC, y, true, rows, cout, 0, 0, 0);
+    if (rc != EWVIT_OK) return rc;
+    return launch_gemm(tmA, tmB, tmC, p, EPI_CONV, (cudaStream_t)stream);
 }
 
 // Debug aid: when non-NULL, CTA 0 of every subsequent GEMM/conv launch writes clock64 stamps of its warp roles

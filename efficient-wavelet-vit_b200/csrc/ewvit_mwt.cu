@@ -183,6 +183,53 @@ __global__ void __launch_bounds__(kHeadThreads) mwt_head_kernel(const HeadParams
     }
 }
 
+// ---- tensor-core head, step 1: high-frequency subbands of one level -> bilinear upsample (F.interpolate,
+//      align_corners=False, mwt.py:79-81; identity at level 1) -> bf16 "padded-flat" NHWC [n, hout+2, wout+2, 16]
+//      (channels 0..8 = the nine subbands in the reference's colour-major order, 9..15 zero; the one-pixel border is
+//      never written and must be zero).  One thread per output pixel: 32 bytes out, coalesced.  Step 2 is the
+//      block-diagonal 9 -> 54 conv on the tensor cores (ewvit_mwt_head_conv_fwd).
+__global__ void __launch_bounds__(256) mwt_upsample_kernel(const float *__restrict__ hf, __nv_bfloat16 *__restrict__ y, long long n,
+                                                           int hin, int win, int hout, int wout, float ry, float rx) {
+    const long long total = n * hout * wout;
+    const bool same = (hin == hout) && (win == wout);
+    const long long plane = (long long)hin * win;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int ox = (int)(i % wout);
+        const long long t = i / wout;
+        const int oy = (int)(t % hout);
+        const long long img = t / hout;
+        const float *src = hf + img * 9 * plane;
+        float v[9];
+        if (same) {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) v[c] = __ldg(src + c * plane + (long long)oy * win + ox);
+        } else {
+            int ya, yb, xa, xb;
+            float ly, lx;
+            src_index(oy, ry, hin, ya, yb, ly);
+            src_index(ox, rx, win, xa, xb, lx);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) {
+                const float *pc = src + c * plane;
+                const float v00 = __ldg(pc + ya * win + xa), v01 = __ldg(pc + ya * win + xb);
+                const float v10 = __ldg(pc + yb * win + xa), v11 = __ldg(pc + yb * win + xb);
+                v[c] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+            }
+        }
+        uint4 lo, hi;
+        __nv_bfloat162 b;
+        b = __floats2bfloat162_rn(v[0], v[1]); lo.x = *reinterpret_cast<uint32_t *>(&b);
+        b = __floats2bfloat162_rn(v[2], v[3]); lo.y = *reinterpret_cast<uint32_t *>(&b);
+        b = __floats2bfloat162_rn(v[4], v[5]); lo.z = *reinterpret_cast<uint32_t *>(&b);
+        b = __floats2bfloat162_rn(v[6], v[7]); lo.w = *reinterpret_cast<uint32_t *>(&b);
+        b = __floats2bfloat162_rn(v[8], 0.f);  hi.x = *reinterpret_cast<uint32_t *>(&b);
+        hi.y = hi.z = hi.w = 0u;
+        uint4 *dst = reinterpret_cast<uint4 *>(y + ((img * (hout + 2) + oy + 1) * (wout + 2) + ox + 1) * 16);
+        dst[0] = lo;
+        dst[1] = hi;
+    }
+}
+
 // 2x2/stride-2 max pool on NHWC bf16; 8 channels (16 bytes) per thread.
 __global__ void maxpool2x2_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ y, long long n, int h,
                                   int w, int c) {
@@ -244,6 +291,22 @@ extern "C" int ewvit_mwt_head_fwd(const float *hf, int n, int hin, int win, int 
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     mwt_head_kernel<<<dim3(tiles, n), kHeadThreads, kHeadSmem, (cudaStream_t)stream>>>(p);
+    EWVIT_LAUNCH_OK();
+    return EWVIT_OK;
+}
+
+extern "C" int ewvit_mwt_upsample_fwd(const float *hf, int n, int hin, int win, int hout, int wout, void *y, void *stream) {
+    EWVIT_REQUIRE(n >= 0 && hin > 0 && win > 0 && hout > 0 && wout > 0, EWVIT_ERR_INVALID_ARG, "ewvit_mwt_upsample_fwd: bad sizes");
+    if (n == 0) return EWVIT_OK;
+    EWVIT_REQUIRE(hf && y && ewvit_aligned16(y), EWVIT_ERR_INVALID_ARG, "ewvit_mwt_upsample_fwd: NULL or misaligned pointer");
+    int rc = ewvit_check_device();
+    if (rc != EWVIT_OK) return rc;
+    const long long total = (long long)n * hout * wout;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)ewvit_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    mwt_upsample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(hf, static_cast<__nv_bfloat16 *>(y), n, hin, win, hout, wout,
+                                                                           (float)hin / (float)hout, (float)win / (float)wout);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }

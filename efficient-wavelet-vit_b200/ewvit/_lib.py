@@ -44,6 +44,8 @@ SIGNATURES = {
     "ewvit_se_apply_nhwc_bf16": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     "ewvit_se_gate_fwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P]),
     "ewvit_conv1x1_gated_nhwc_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, c_int, P, P, P]),
+    "ewvit_mwt_upsample_fwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "ewvit_mwt_head_conv_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P]),
     "ewvit_debug_set_trace": (c_int, [P]),
     "ewvit_debug_set_flags": (c_int, [c_int]),
     "ewvit_video_head_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P, P, P, P, P, c_int, P, P]),

@@ -109,6 +109,18 @@ class MwtRunner:
         self.head_w = torch.stack([sd[f"hf_conv.seperate.{i}.0.weight"].float() for i in range(3)]).contiguous()
         sc, sh = zip(*[_fold_bn(sd, f"hf_conv.seperate.{i}.0.", f"hf_conv.seperate.{i}.1.") for i in range(3)])
         self.head_scale, self.head_shift = torch.cat(sc).contiguous(), torch.cat(sh).contiguous()
+        # tensor-core head: the three convs as one block-diagonal [64, 3 x 64] bf16 matrix, k = dy*64 + dx*16 + (3g + ic)
+        wbd = torch.zeros((64, 3, 4, 16), dtype=torch.float32, device=dev)
+        for g in range(3):
+            wg = self.head_w[g]                                   # [18, 3, ky, kx]
+            wbd[g * 18:(g + 1) * 18, :, :3, g * 3:(g + 1) * 3] = wg.permute(0, 2, 3, 1)
+        self.head_wbd = wbd.reshape(64, 192).to(torch.bfloat16).contiguous()
+        self.head_scale64 = torch.zeros(64, dtype=torch.float32, device=dev)
+        self.head_shift64 = torch.zeros(64, dtype=torch.float32, device=dev)
+        self.head_scale64[:54] = self.head_scale
+        self.head_shift64[:54] = self.head_shift
+        import os
+        self.head_tc = os.environ.get("EWVIT_HEAD", "tc") != "simt"
         self.fus_w = _conv_w_tapmajor(sd["hf_conv.fusion.0.weight"], 64)
         self.fus_scale, self.fus_shift = _fold_bn(sd, "hf_conv.fusion.0.", "hf_conv.fusion.1.")
         self.ms_w = _conv_w_tapmajor(sd["multiscale_fusion.0.weight"])
@@ -131,6 +143,7 @@ class MwtRunner:
             h4, w4 = (h2 // 2 - 1) // 2 + 1, (w2 // 2 - 1) // 2 + 1  # maxpool then stride-2 conv
             ws = {
                 "hf": [torch.empty((n, 3, 3, h >> l, w >> l), dtype=torch.float32, device=dev) for l in (1, 2, 3)],
+                "up": torch.zeros((n, h1 + 2, w1 + 2, 16), dtype=bf, device=dev),        # zero border, kept zero
                 "head": torch.zeros((n, h1 + 2, w1 + 2, 64), dtype=bf, device=dev),      # zero border, kept zero
                 "cat": torch.empty((n, h1 + 2, w1 + 2, 3 * d), dtype=bf, device=dev),
                 "ms": torch.empty((n, h1 + 2, w1 + 2, d), dtype=bf, device=dev),
@@ -153,8 +166,12 @@ class MwtRunner:
             ops.dwt3_haar(frames, out={"hf1": hf[0], "hf2": hf[1], "hf3": hf[2]}, want=("hf1", "hf2", "hf3"))
         for lvl in range(3):
             with stage("mwt.head"):
-                ops.mwt_head(hf[lvl].view(n, 9, h >> (lvl + 1), w >> (lvl + 1)), self.head_w, self.head_scale,
-                             self.head_shift, ws["head"], h1, w1)
+                hfl = hf[lvl].view(n, 9, h >> (lvl + 1), w >> (lvl + 1))
+                if self.head_tc:
+                    ops.mwt_upsample(hfl, ws["up"], h1, w1)
+                    ops.mwt_head_conv(ws["up"], self.head_wbd, self.head_scale64, self.head_shift64, ws["head"], h1, w1)
+                else:
+                    ops.mwt_head(hfl, self.head_w, self.head_scale, self.head_shift, ws["head"], h1, w1)
             with stage("mwt.hf_fusion"):
                 ops.conv3x3_bf16(ws["head"], self.fus_w, n, h1, w1, 1, True, self.fus_scale, self.fus_shift, True,
                                  ws["cat"], lvl * d, True)

@@ -163,6 +163,35 @@ def mwt_head(hf, w, scale, shift, y, hout, wout):
     return y
 
 
+def mwt_upsample(hf, up, hout, wout):
+    """hf [n,9,hin,win] fp32 -> up [n,hout+2,wout+2,16] bf16 (interior written, channels 9..15 zero)."""
+    _check_f32(hf, "hf")
+    _check_bf16(up, "up")
+    n, c9, hin, win = hf.shape
+    if c9 != 9 or up.numel() != n * (hout + 2) * (wout + 2) * 16:
+        raise EwvitError("mwt_upsample: expects 9 subband planes and an [n,hout+2,wout+2,16] output")
+    with torch.cuda.device(hf.device):
+        check(load().ewvit_mwt_upsample_fwd(hf.data_ptr(), n, hin, win, hout, wout, up.data_ptr(), _stream()), "ewvit_mwt_upsample_fwd")
+    return up
+
+
+def mwt_head_conv(up, w, scale, shift, y, h, wd):
+    """up [n,h+2,wd+2,16] bf16, w [64,192] bf16, scale/shift [64] fp32 -> y [n,h+2,wd+2,64] bf16 (see include/ewvit.h)."""
+    _check_bf16(up, "up")
+    _check_bf16(w, "w", 2)
+    _check_bf16(y, "y")
+    _check_f32(scale, "scale")
+    _check_f32(shift, "shift")
+    n = up.numel() // ((h + 2) * (wd + 2) * 16)
+    if up.numel() != n * (h + 2) * (wd + 2) * 16 or y.numel() != n * (h + 2) * (wd + 2) * 64 or tuple(w.shape) != (64, 192) \
+            or scale.numel() != 64 or shift.numel() != 64:
+        raise EwvitError("mwt_head_conv: shape mismatch")
+    with torch.cuda.device(up.device):
+        check(load().ewvit_mwt_head_conv_fwd(up.data_ptr(), w.data_ptr(), n, h, wd, scale.data_ptr(), shift.data_ptr(), y.data_ptr(),
+                                             _stream()), "ewvit_mwt_head_conv_fwd")
+    return y
+
+
 def maxpool2x2(x, y=None):
     """NHWC bf16 [n,h,w,c] -> [n,h/2,w/2,c]."""
     _check_bf16(x, "x", 4)

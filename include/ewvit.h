@@ -139,6 +139,18 @@ EWVIT_API int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, int
 EWVIT_API int ewvit_mwt_head_fwd(const float *hf, int n, int hin, int win, int hout, int wout, const float *w,
                                  const float *scale, const float *shift, void *y, void *stream);
 
+/* Tensor-core variant of the high-frequency head (same reference lines, network/mwt.py:77-86), in two steps:
+ *   1. ewvit_mwt_upsample_fwd: hf [n, 9, hin, win] fp32 -> bilinear upsample (identity when hin == hout) ->
+ *      up [n, hout+2, wout+2, 16] bf16 padded-flat NHWC (channels 9..15 zero).  Only interior pixels are written: the
+ *      one-pixel border must be zero (zero the buffer once).
+ *   2. ewvit_mwt_head_conv_fwd: the three Conv2d(3->18,3x3,p1)+BN+ReLU as one block-diagonal conv on the tensor cores.
+ *      w [64, 192] bf16 with w[g*18+oc][dy*64 + dx*16 + g*3+ic] = seperate[g].weight[oc][ic][dy][dx] (zero elsewhere),
+ *      scale/shift [64] fp32 (folded bias + eval BatchNorm, zeros past channel 54),
+ *      y [n, h+2, wd+2, 64] bf16 padded-flat NHWC (channels 54..63 and the border come out as zeros). */
+EWVIT_API int ewvit_mwt_upsample_fwd(const float *hf, int n, int hin, int win, int hout, int wout, void *up, void *stream);
+EWVIT_API int ewvit_mwt_head_conv_fwd(const void *up, const void *w, int n, int h, int wd, const float *scale,
+                                      const float *shift, void *y, void *stream);
+
 /* nn.MaxPool2d(2, 2) on NHWC bf16 (freq_pool[0], mwt.py:39): x [n,h,w,c] -> y [n,h/2,w/2,c]. */
 EWVIT_API int ewvit_maxpool2x2_nhwc_bf16(const void *x, int64_t n, int h, int w, int c, void *y, void *stream);
 

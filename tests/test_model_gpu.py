@@ -68,6 +68,17 @@ def test_mwt_head_kernel(dama_sd, sd_cuda, frames):
         check(f"mwt_head level {lvl + 1}", got[:, 1:-1, 1:-1, :54].permute(0, 3, 1, 2), ref, 1e-2)
         assert float(got[:, 1:-1, 1:-1, 54:].abs().max()) == 0.0
         assert float(got[:, 0].abs().max()) == 0.0 and float(got[:, :, -1].abs().max()) == 0.0
+        # tensor-core variant: bf16 upsampled planes -> block-diagonal conv through TMA's overlapping-window map
+        up = torch.zeros((2, 114, 114, 16), dtype=torch.bfloat16, device="cuda")
+        y2 = torch.full((2, 114, 114, 64), 7.0, dtype=torch.bfloat16, device="cuda")     # borders must come out as zeros
+        ops.mwt_upsample(hf.view(2, 9, hf.shape[-2], hf.shape[-1]), up, 112, 112)
+        check(f"mwt_upsample level {lvl + 1}", up.float().cpu()[:, 1:-1, 1:-1, :9].permute(0, 3, 1, 2), hf9, 1e-2)
+        assert float(up[:, :, :, 9:].abs().max()) == 0.0 and float(up[:, 0].abs().max()) == 0.0
+        ops.mwt_head_conv(up, run.head_wbd, run.head_scale64, run.head_shift64, y2, 112, 112)
+        got2 = y2.float().cpu()
+        check(f"mwt_head_conv level {lvl + 1}", got2[:, 1:-1, 1:-1, :54].permute(0, 3, 1, 2), ref, 2e-2)
+        assert float(got2[:, 1:-1, 1:-1, 54:].abs().max()) == 0.0
+        assert float(got2[:, 0].abs().max()) == 0.0 and float(got2[:, :, -1].abs().max()) == 0.0 and float(got2[:, -1].abs().max()) == 0.0
 
 
 def test_mwt_forward(dama_sd, sd_cuda, frames, golden):
