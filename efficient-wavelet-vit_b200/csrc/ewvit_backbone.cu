@@ -15,7 +15,7 @@ __device__ __forceinline__ float silu(float x) { return ewvit::silu_fast(x); }
 constexpr int kStemMaxC = 32;
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                         const float *__restrict__ bias, __nv_bfloat16 *__restrict__ y,
-                                                        int n, int h, int wd, int ho, int wo, int cout) {
+                                                        int n, int h, int wd, int ho, int wo, int cout, int pad) {
     __shared__ float s_w[kStemMaxC * 27];
     __shared__ float s_b[kStemMaxC];
     for (int i = threadIdx.x; i < cout * 27; i += blockDim.x) s_w[i] = w[i];
@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict_
                     const int iy = 2 * oy + dy - 1, ix = 2 * ox + dx - 1;
                     in[c * 9 + dy * 3 + dx] = (iy >= 0 && iy < h && ix >= 0 && ix < wd) ? __ldg(x + ((img * 3 + c) * h + iy) * wd + ix) : 0.f;
                 }
-        __nv_bfloat16 *py = y + idx * cout;
+        // pad = 1: padded-flat output [n, ho+2, wo+2, cout] (interior written, the zero border belongs to the caller)
+        __nv_bfloat16 *py = y + ((img * (ho + 2 * pad) + oy + pad) * (wo + 2 * pad) + ox + pad) * cout;
         for (int c0 = 0; c0 < cout; c0 += 8) {
             float o[8];
 #pragma unroll
@@ -342,8 +343,8 @@ __global__ void __launch_bounds__(256) se_scale_kernel(__nv_bfloat16 *__restrict
 
 }  // namespace
 
-extern "C" int ewvit_stem_conv_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
-                                   void *y, void *stream) {
+static int stem_impl(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout, void *y, int out_padded,
+                     void *stream) {
     EWVIT_REQUIRE(n >= 0 && h > 0 && wd > 0, EWVIT_ERR_INVALID_ARG, "ewvit_stem_conv_fwd: bad sizes");
     if (n == 0) return EWVIT_OK;
     EWVIT_REQUIRE(x && w && bias && y && ewvit_aligned16(y), EWVIT_ERR_INVALID_ARG, "ewvit_stem_conv_fwd: NULL or misaligned pointer");
@@ -355,9 +356,19 @@ extern "C" int ewvit_stem_conv_fwd(const float *x, int n, int h, int wd, const f
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)ewvit_num_sms() * 32;
     if (blocks > cap) blocks = cap;
-    stem_conv_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, w, bias, static_cast<__nv_bfloat16 *>(y), n, h, wd, ho, wo, cout);
+    stem_conv_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, w, bias, static_cast<__nv_bfloat16 *>(y), n, h, wd, ho, wo, cout, out_padded ? 1 : 0);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
+}
+
+extern "C" int ewvit_stem_conv_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
+                                   void *y, void *stream) {
+    return stem_impl(x, n, h, wd, w, bias, cout, y, 0, stream);
+}
+
+extern "C" int ewvit_stem_conv_padded_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
+                                          void *y, void *stream) {
+    return stem_impl(x, n, h, wd, w, bias, cout, y, 1, stream);
 }
 
 template <int SC, int STRIDE>

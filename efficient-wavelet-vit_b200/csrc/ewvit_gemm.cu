@@ -101,6 +101,7 @@ struct GemmParams {
                          // kFlat3Rows activation rows and the three weight tiles of dx = 0,1,2; the three A operands are the
                          // same window read at a start address shifted by 0/1/2 rows, so every activation row crosses
                          // L2 -> shared memory 3 times per tile instead of 9
+    int b_tile_bytes;    // bytes of one B tile = rows of the tmB box x 128 (0 = kBN rows)
     int stage_bytes;     // ring slot size: A tile (+ B tile unless the weights are resident)
     int b_res;           // A_IM2COL: all k-blocks of B stay resident in shared memory (loaded once per CTA)
     int bres_off;        // byte offset of the resident B region
@@ -165,7 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     unsigned long long *hfull = bars + 2 * kStages + 2 * kAccStages, *hempty = hfull + kMaxHalo;
     unsigned long long *bres_bar = hempty + kMaxHalo;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bres_bar + 1);
-    constexpr int kBTileB = kBN * BK * 2;               // B tile of this column width
+    const uint32_t kBTileB = (uint32_t)p.b_tile_bytes;    // B tile: b_rows x 64 bf16 (b_rows = kBN, or the 16-aligned N of a single column tile)
     constexpr uint32_t kTmemColsT = kAccStages * kBN;
     __shared__ __align__(16) float s_scale[2 * kBN], s_shift[2 * kBN];
     __shared__ int s_koff[kBuilder ? 9 * 8 : 1];
@@ -662,7 +663,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int i = 0; i < 8; ++i) f8[i] = fmaxf(f8[i], 0.f);
                         }
-                        if (p.residual_bf16) {   // skip connection is added AFTER the activation (zeros past N / past M)
+                        if (zero) {              // padded-flat output: the one-pixel border stays zero
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f8[i] = 0.f;
+                        } else if (p.residual_bf16) {   // skip connection is added AFTER the activation (zeros past N / past M)
                             const __nv_bfloat162 *rp = reinterpret_cast<const __nv_bfloat162 *>(&rcur[g8]);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -808,6 +812,14 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ partial, int spli
     }
 }
 
+// Rows of the B (weight) box: a single column tile only needs the 16-aligned number of output channels -- the MMA reads
+// n_valid rows -- which shrinks the resident filter bank / ring slots and so deepens the activation ring.
+static inline int b_box_rows(int N, int bn, int tiles_n) {
+    if (tiles_n != 1) return bn;
+    const int r = (N + 15) & ~15;
+    return r < bn ? r : bn;
+}
+
 static long long *g_trace = nullptr;
 static int g_dbg = 0;
 
@@ -820,19 +832,20 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
         EWVIT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kBuilder, kBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kEpi, kBuilder>::kSmemBytes));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    if (p.stage_bytes <= 0) p.stage_bytes = kTileBytes + kBN * BK * 2;
+    if (p.b_tile_bytes <= 0) p.b_tile_bytes = kBN * BK * 2;
+    if (p.stage_bytes <= 0) p.stage_bytes = kTileBytes + p.b_tile_bytes;
     if (p.stages <= 0) {
-        p.stages = Cfg<kEpi, kBuilder>::kOperandBytes / (kTileBytes + kBN * BK * 2);
+        p.stages = Cfg<kEpi, kBuilder>::kOperandBytes / p.stage_bytes;
         if (p.stages > 6) p.stages = 6;
     }
     // plain (one-tap-per-slot) paths with a single column tile and a small weight matrix: keep all of B resident and let
     // the ring carry activation tiles only -- TMA's ~1.5 us latency makes throughput = bytes in flight / latency, and a
     // slot without its B tile is half the size
     if (!kBuilder && !p.flat3 && !p.b_res && p.tiles_n == 1 && p.splits == 1 && !(g_dbg & 64) &&
-        p.num_kb * kBN * BK * 2 <= 96 * 1024 && p.stage_bytes == kTileBytes + kBN * BK * 2) {
+        p.num_kb * p.b_tile_bytes <= 96 * 1024 && p.stage_bytes == kTileBytes + p.b_tile_bytes) {
         p.b_res = 1;
         p.stage_bytes = kTileBytes;
-        p.stages = (Cfg<kEpi, kBuilder>::kOperandBytes - p.num_kb * kBN * BK * 2) / kTileBytes;
+        p.stages = (Cfg<kEpi, kBuilder>::kOperandBytes - p.num_kb * p.b_tile_bytes) / kTileBytes;
         if (p.stages > kStages) p.stages = kStages;
         p.bres_off = p.stages * kTileBytes;
     }
@@ -1089,8 +1102,8 @@ extern "C" int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, in
 // General NHWC bf16 convolution for the EfficientNet backbone (1x1 or 3x3/pad 1, stride 1 or 2) with a fused
 // bias + optional bf16 residual + activation epilogue.  Channel counts only need to be multiples of 8: the K and N
 // tails are zero-filled by TMA (boxes may overhang the tensor) and masked in the epilogue.
-extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, int wd, int cin, int cout, int ksize,
-                                    int stride, const float *bias, int act, const void *residual, void *y, void *stream) {
+static int conv_nhwc_impl(const void *x, const void *w, int n, int h, int wd, int cin, int cout, int ksize, int stride,
+                          const float *bias, int act, const void *residual, void *y, int in_padded, int out_padded, void *stream) {
     EWVIT_REQUIRE(n >= 0 && h > 0 && wd > 0 && cin > 0 && cout > 0, EWVIT_ERR_INVALID_ARG, "ewvit_conv_nhwc_bf16: bad sizes");
     if (n == 0) return EWVIT_OK;
     EWVIT_REQUIRE(x && w && y, EWVIT_ERR_INVALID_ARG, "ewvit_conv_nhwc_bf16: NULL pointer");
@@ -1109,24 +1122,60 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
     // column tile: 256 wide when cout > 128, so A is fetched (or assembled) once per 256 output channels
     // (the stride-2 halo of the assembled path is 4x larger: keep 128-wide tiles there so two halo buffers still fit)
     const int bn = (cout > 128 && !(ksize == 3 && cin < BK && stride == 2)) ? 256 : 128;
-    const int stage_bytes = kTileBytes + bn * BK * 2;
     p.N = cout;
     p.tiles_n = (cout + bn - 1) / bn;
+    const int brows = b_box_rows(cout, bn, p.tiles_n);
+    p.b_tile_bytes = brows * BK * 2;
+    const int stage_bytes = kTileBytes + p.b_tile_bytes;
     p.splits = 1;
     p.out = y; p.out_fp32 = 0; p.ldo = cout; p.col_off = 0;
     p.shift = bias; p.act = act;
     p.residual_bf16 = static_cast<const __nv_bfloat16 *>(residual);
     p.ldr = cout;
     CUtensorMap tmA, tmB;
-    if (ksize == 1) {
-        const long long rows = (long long)n * h * wd;
+    const bool ow = ksize == 3 && stride == 1 && cin < BK && in_padded && out_padded;
+    EWVIT_REQUIRE(in_padded == out_padded || (ksize == 3 && cin < BK), EWVIT_ERR_UNSUPPORTED,
+                  "ewvit_conv_nhwc_bf16_ex: only the small-channel 3x3 convs may change the padding of the layout");
+    EWVIT_REQUIRE(!(in_padded || out_padded) || ksize == 1 || cin < BK, EWVIT_ERR_UNSUPPORTED,
+                  "ewvit_conv_nhwc_bf16_ex: padded layouts are implemented for 1x1 convs and 3x3 convs with cin < 64");
+    long long flat_rows = 0;
+    if (ow) {
+        // "overlapping window" 3x3 conv on padded-flat tensors: with cin < 64 the three horizontal taps of an output pixel
+        // are 3*cin CONTIGUOUS elements, so the im2col row of a vertical tap is a window of a tensor map whose rows are
+        // 3*cin long but only cin apart; k-blocks = (dy, 64-element piece of the window), columns past 3*cin zero-filled.
+        // No builder warps: this is the plain TMA -> MMA pipeline with the four-group epilogue.
+        const int hin = h + 2, win = wd + 2;
+        const long long rows = (long long)n * hin * win;
+        const int nsub = (3 * cin + BK - 1) / BK;
+        uint64_t dims[2] = {(uint64_t)3 * cin, (uint64_t)(rows - 2)}, str[2] = {2, (uint64_t)cin * 2};
+        uint32_t box[2] = {BK, BM};
+        rc = ewvit_make_tmap_bf16(&tmA, x, 2, dims, str, box, nullptr);
+        if (rc != EWVIT_OK) return rc;
+        uint64_t dimsb[2] = {(uint64_t)3 * nsub * BK, (uint64_t)cout}, strb[2] = {2, (uint64_t)3 * nsub * BK * 2};
+        uint32_t boxb[2] = {BK, (uint32_t)brows};
+        rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, strb, boxb, nullptr);
+        if (rc != EWVIT_OK) return rc;
+        p.a_mode = A_FLAT;
+        p.chunks_per_tap = nsub;
+        p.num_kb = 3 * nsub;
+        p.kb_per_split = p.num_kb;
+        for (int dy = 0; dy < 3; ++dy) p.tap_a0[dy] = (dy - 1) * win - 1;
+        p.M = rows;
+        p.tiles_m = (int)((rows + BM - 1) / BM);
+        p.pad_hp = hin;
+        p.pad_wp = win;
+        flat_rows = rows;
+    } else if (ksize == 1) {
+        const long long rows = in_padded ? (long long)n * (h + 2) * (wd + 2) : (long long)n * h * wd;
+        if (in_padded) { p.pad_hp = h + 2; p.pad_wp = wd + 2; }
+        flat_rows = rows;
         const int num_kb = (cin + BK - 1) / BK;
         uint64_t dims[2] = {(uint64_t)cin, (uint64_t)rows}, str[2] = {2, (uint64_t)cin * 2};
         uint32_t box[2] = {BK, BM};
         rc = ewvit_make_tmap_bf16(&tmA, x, 2, dims, str, box, nullptr);
         if (rc != EWVIT_OK) return rc;
         uint64_t dimsb[2] = {(uint64_t)cin, (uint64_t)cout};
-        uint32_t boxb[2] = {BK, (uint32_t)bn};
+        uint32_t boxb[2] = {BK, (uint32_t)brows};
         rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, str, boxb, nullptr);
         if (rc != EWVIT_OK) return rc;
         p.a_mode = A_FLAT;
@@ -1141,7 +1190,7 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
         const int kdense = 9 * cin;
         const int num_kb = (kdense + BK - 1) / BK;
         uint64_t dimsb[2] = {(uint64_t)num_kb * BK, (uint64_t)cout}, strb[2] = {2, (uint64_t)num_kb * BK * 2};
-        uint32_t boxb[2] = {BK, (uint32_t)bn};
+        uint32_t boxb[2] = {BK, (uint32_t)brows};
         rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, strb, boxb, nullptr);
         if (rc != EWVIT_OK) return rc;
         const int box_w = 16, box_h = 8;
@@ -1152,9 +1201,9 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
         p.tiles_y = (ho + box_h - 1) / box_h;
         p.tiles_m = p.tiles_x * p.tiles_y * n;
         p.out_w = wo; p.out_h = ho;
-        p.out_pad = 0;
-        p.out_wp = wo;
-        p.out_img_rows = (long long)ho * wo;
+        p.out_pad = out_padded ? 1 : 0;
+        p.out_wp = wo + 2 * p.out_pad;
+        p.out_img_rows = (long long)(ho + 2 * p.out_pad) * p.out_wp;
         p.M = (long long)n * p.out_img_rows;
         p.num_kb = num_kb;
         p.kb_per_split = num_kb;
@@ -1170,11 +1219,11 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
             p.plane_bytes = (plane_payload + 127) & ~127;                // TMA destinations must be 128-byte aligned
             p.halo_bytes = p.halo_nb * plane_payload;                   // bytes the TMA unit reports on the mbarrier
             p.halo_stride = (p.halo_nb * p.plane_bytes + 1023) & ~1023;
-            p.b_res = (p.tiles_n == 1 && num_kb * bn * BK * 2 <= 64 * 1024) ? 1 : 0;
+            p.b_res = (p.tiles_n == 1 && num_kb * p.b_tile_bytes <= 64 * 1024) ? 1 : 0;
             int sbytes = stage_bytes, reserve = 0;
             if (p.b_res) {                      // ring slots hold A only; the weights get their own region
                 sbytes = kTileBytes;
-                reserve = num_kb * bn * BK * 2;
+                reserve = num_kb * p.b_tile_bytes;
             }
             p.stage_bytes = sbytes;
             p.stages = bn == 256 ? 3 : 4;
@@ -1185,10 +1234,14 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
             p.bres_off = p.stages * sbytes + p.halo_bufs * p.halo_stride;
             p.chunks_per_tap = 1;
             // activation viewed as [n][h][wd*cin]: a run of pixels of one image row is one contiguous TMA row
+            // (a padded-flat input is addressed through its interior: same extents, the pitches of the padded tensor)
+            const int hpi = in_padded ? h + 2 : h, wpi = in_padded ? wd + 2 : wd;
+            const void *xin = in_padded ? static_cast<const void *>(static_cast<const __nv_bfloat16 *>(x) + ((size_t)wpi + 1) * cin) : x;
+            EWVIT_REQUIRE(ewvit_aligned16(xin), EWVIT_ERR_UNSUPPORTED, "ewvit_conv_nhwc_bf16_ex: interior of the padded input is not 16-byte aligned");
             uint64_t dims3[3] = {(uint64_t)wd * cin, (uint64_t)h, (uint64_t)n};
-            uint64_t str3[3] = {2, (uint64_t)wd * cin * 2, (uint64_t)h * wd * cin * 2};
+            uint64_t str3[3] = {2, (uint64_t)wpi * cin * 2, (uint64_t)hpi * wpi * cin * 2};
             uint32_t box3[3] = {(uint32_t)(p.halo_ppb * cin), (uint32_t)p.halo_h, 1};
-            rc = ewvit_make_tmap_bf16(&tmA, x, 3, dims3, str3, box3, nullptr, /*swizzle128=*/false);
+            rc = ewvit_make_tmap_bf16(&tmA, xin, 3, dims3, str3, box3, nullptr, /*swizzle128=*/false);
             if (rc != EWVIT_OK) return rc;
         } else {
             p.a_mode = A_TILE4D;
@@ -1205,12 +1258,23 @@ extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, 
         }
     }
     CUtensorMap tmC;
-    if (ksize == 1)
-        rc = make_out_tmap(&tmC, y, true, (long long)n * h * wd, cout, 0, 0, 0);
+    if (flat_rows)
+        rc = make_out_tmap(&tmC, y, true, flat_rows, cout, 0, 0, 0);
     else
-        rc = make_out_tmap(&tmC, y, false, 0, cout, n, ho, wo);
+        rc = make_out_tmap(&tmC, y, false, 0, cout, n, ho + 2 * p.out_pad, wo + 2 * p.out_pad, ho + p.out_pad, wo + p.out_pad);
     if (rc != EWVIT_OK) return rc;
     return launch_gemm(tmA, tmB, tmC, p, EPI_BB, (cudaStream_t)stream, bn);
+}
+
+extern "C" int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, int wd, int cin, int cout, int ksize,
+                                    int stride, const float *bias, int act, const void *residual, void *y, void *stream) {
+    return conv_nhwc_impl(x, w, n, h, wd, cin, cout, ksize, stride, bias, act, residual, y, 0, 0, stream);
+}
+
+extern "C" int ewvit_conv_nhwc_bf16_ex(const void *x, const void *w, int n, int h, int wd, int cin, int cout, int ksize,
+                                       int stride, const float *bias, int act, const void *residual, void *y, int in_padded,
+                                       int out_padded, void *stream) {
+    return conv_nhwc_impl(x, w, n, h, wd, cin, cout, ksize, stride, bias, act, residual, y, in_padded ? 1 : 0, out_padded ? 1 : 0, stream);
 }
 
 // Tensor-core head of one wavelet level, step 2 (mwt.py:84-86): the three per-colour Conv2d(3->18, 3x3, p1)+BN+ReLU as
@@ -1255,7 +1319,8 @@ extern "C" int ewvit_mwt_head_conv_fwd(const void *up, const void *w, int n, int
         rc = ewvit_make_tmap_bf16(&tmA, up, 2, dims, str, box, nullptr);
         if (rc != EWVIT_OK) return rc;
         uint64_t dimsb[2] = {(uint64_t)3 * BK, (uint64_t)cout}, strb[2] = {2, (uint64_t)3 * BK * 2};
-        uint32_t boxb[2] = {BK, BN};
+        uint32_t boxb[2] = {BK, (uint32_t)cout};
+        p.b_tile_bytes = cout * BK * 2;
         rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, strb, boxb, nullptr);
         if (rc != EWVIT_OK) return rc;
     }
@@ -1312,11 +1377,14 @@ extern "C" int ewvit_conv1x1_gated_nhwc_bf16(const void *x, const float *gate, c
     p.shift = bias; p.act = act;
     p.residual_bf16 = static_cast<const __nv_bfloat16 *>(residual);
     p.ldr = cout;
-    p.stage_bytes = kTileBytes + bn * BK * 2;
-    p.stages = bn == 256 ? 4 : 6;
+    const int brows = b_box_rows(cout, bn, p.tiles_n);
+    p.b_tile_bytes = brows * BK * 2;
+    p.stage_bytes = kTileBytes + p.b_tile_bytes;
+    p.stages = Cfg<EPI_BB, true>::kOperandBytes / p.stage_bytes;
+    if (p.stages > 6) p.stages = 6;
     CUtensorMap tmA, tmB, tmC;
     uint64_t dimsa[2] = {(uint64_t)cin, (uint64_t)rows}, dimsb[2] = {(uint64_t)cin, (uint64_t)cout}, str[2] = {2, (uint64_t)cin * 2};
-    uint32_t boxa[2] = {BK, BM}, boxb[2] = {BK, (uint32_t)bn};
+    uint32_t boxa[2] = {BK, BM}, boxb[2] = {BK, (uint32_t)brows};
     rc = ewvit_make_tmap_bf16(&tmA, x, 2, dimsa, str, boxa, nullptr);
     if (rc != EWVIT_OK) return rc;
     rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, str, boxb, nullptr);

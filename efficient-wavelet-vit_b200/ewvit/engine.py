@@ -235,6 +235,16 @@ def _w3x3_tapmajor_padded(w):
     return out.contiguous()
 
 
+def _w3x3_window_packed(w):
+    """[cout, cin, 3, 3] fp32 (cin < 64) -> bf16 [cout, 3*nsub*64] for the overlapping-window conv path:
+    k = dy*(nsub*64) + dx*cin + c with nsub = ceil(3*cin/64), zero elsewhere (ewvit_conv_nhwc_bf16_ex)."""
+    cout, cin = w.shape[:2]
+    nsub = (3 * cin + 63) // 64
+    out = torch.zeros((cout, 3, nsub * 64), dtype=torch.bfloat16, device=w.device)
+    out[:, :, :3 * cin] = w.permute(0, 2, 3, 1).reshape(cout, 3, 3 * cin).to(torch.bfloat16)     # [cout, dy, (dx, c)]
+    return out.reshape(cout, 3 * nsub * 64).contiguous()
+
+
 class NativeEffNetV2:
     """torchvision ``efficientnet_v2_s(...).features`` (sfe.py:111-113,150) in eval mode on the native kernels:
     FusedMBConv 3x3 convs, 1x1 expand/project convs and the 1x1 head on the tcgen05 implicit-GEMM kernel with
@@ -247,6 +257,8 @@ class NativeEffNetV2:
         self.device = dev
         self.ops = []
         self.fuse_se = os.environ.get("EWVIT_SE_FUSED", "1") == "1"
+        self.win_w, self.cin3 = {}, {}      # op index -> window-packed weights / input channels of the 3x3 convs
+        self._padbuf = {}
         mods = list(features)
         stem = mods[0]
         w, b = _fold_conv_bn(stem[0], stem[1])
@@ -262,6 +274,12 @@ class NativeEffNetV2:
                     c0 = layers[0]
                     w, b = _fold_conv_bn(c0[0], c0[1])
                     stride = c0[0].stride[0]
+                    # candidate for the overlapping-window path (needs padded layouts).  Measured: 48 -> 192 @56^2 0.52 -> 0.36 ms,
+                    # but 24 -> 24 @112^2 0.63 -> 0.85 ms (its 48-byte pixel pitch makes every 128-byte TMA row straddle two
+                    # cache lines and K pads 72 -> 128 per tap row), so the 24-channel layers stay on the assembled-A path
+                    if 32 <= w.shape[1] < 64 and stride == 1:
+                        self.win_w[len(self.ops)] = _w3x3_window_packed(w).to(dev)
+                    self.cin3[len(self.ops)] = int(w.shape[1])
                     if len(layers) == 1:
                         self.ops.append(("conv3", _w3x3_tapmajor_padded(w).to(dev), b.to(dev), stride, "silu", res, True))
                     else:
@@ -288,6 +306,55 @@ class NativeEffNetV2:
         head = mods[-1]
         w, b = _fold_conv_bn(head[0], head[1])
         self.ops.append(("conv1", w.flatten(1).to(torch.bfloat16).to(dev).contiguous(), b.to(dev), "silu", False, False))
+        self.layout = self._plan_layouts(os.environ.get("EWVIT_WINDOW_CONV", "1") == "1")
+
+    def _plan_layouts(self, enable):
+        """Per op (in_padded, out_padded).  The stride-1 3x3 convs with cin < 64 (stages 1-2 of V2-S) run fastest on
+        "padded-flat" tensors [n, h+2, w+2, c] (overlapping-window TMA path, no im2col); the 1x1 convs between them keep
+        that layout, the stride-2 small-channel convs convert (they read the interior of a padded input and can write
+        either layout).  Falls back to plain layouts everywhere if a padded tensor would reach an op that cannot take it."""
+        plain = [(False, False)] * len(self.ops)
+        if not enable:
+            return plain
+
+        def wants_padded(j):
+            while j < len(self.ops) and self.ops[j][0] == "conv1":
+                j += 1
+            return j < len(self.ops) and self.ops[j][0] == "conv3" and j in self.win_w
+
+        plan, padded = [], False
+        for i, op in enumerate(self.ops):
+            kind = op[0]
+            if kind == "stem":
+                plan.append((False, wants_padded(i + 1)))
+            elif kind == "conv3":
+                if i in self.win_w and padded:
+                    plan.append((True, True))
+                elif self.cin3[i] < 64:
+                    plan.append((padded, wants_padded(i + 1)))
+                elif padded:
+                    return plain
+                else:
+                    plan.append((False, False))
+            elif kind == "conv1":
+                plan.append((padded, padded))
+            else:
+                if padded:
+                    return plain
+                plan.append((False, False))
+            padded = plan[-1][1]
+        return plain if padded else plan
+
+    def _zero_bordered(self, i, shape):
+        """Persistent output buffer of op i whose border is zeroed once (the op rewrites the interior every call)."""
+        key = (i, shape)
+        t = self._padbuf.get(key)
+        if t is None:
+            if len(self._padbuf) > 16:
+                self._padbuf.clear()
+            t = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
+            self._padbuf[key] = t
+        return t
 
     def forward(self, frames):
         """fp32 [n,3,H,W] -> bf16 NHWC [n, H/32, W/32, C_out]."""
@@ -298,17 +365,36 @@ class NativeEffNetV2:
         for i, op in enumerate(self.ops):
             kind = op[0]
             with stage(f"bb.{kind}" if TIMER is None or not getattr(TIMER, "per_layer", False) else f"bb.{i:03d}.{kind}"):
+                in_p, out_p = self.layout[i]
                 if kind == "stem":
-                    x = ops.stem_conv(frames, op[1], op[2])
+                    if out_p:
+                        n, _, h, wd = frames.shape
+                        buf = self._zero_bordered(i, (n, (h - 1) // 2 + 3, (wd - 1) // 2 + 3, op[1].shape[0]))
+                        x = ops.stem_conv(frames, op[1], op[2], out=buf, out_padded=True)
+                    else:
+                        x = ops.stem_conv(frames, op[1], op[2])
                     block_in = x
                 elif kind == "conv3":
                     _, w, b, stride, act, res, ends = op
-                    x = ops.conv_nhwc_bf16(x, w, 3, stride, bias=b, act=act, residual=block_in if res else None)
+                    if in_p or out_p:
+                        window = in_p and out_p and i in self.win_w
+                        out = None
+                        if out_p and not window:       # stride-2 conv into a padded layout: interior only
+                            n, hp, wp = x.shape[0], x.shape[1] - 2 * in_p, x.shape[2] - 2 * in_p
+                            out = self._zero_bordered(i, (n, (hp - 1) // stride + 3, (wp - 1) // stride + 3, w.shape[0]))
+                        x = ops.conv_nhwc_bf16_ex(x, self.win_w[i] if window else w, 3, stride, self.cin3[i], bias=b, act=act,
+                                                  residual=block_in if res else None, out=out, in_padded=in_p, out_padded=out_p)
+                    else:
+                        x = ops.conv_nhwc_bf16(x, w, 3, stride, bias=b, act=act, residual=block_in if res else None)
                     if ends:
                         block_in = x
                 elif kind == "conv1":
                     _, w, b, act, res, ends = op
-                    x = ops.conv_nhwc_bf16(x, w, 1, 1, bias=b, act=act, residual=block_in if res else None)
+                    if in_p:
+                        x = ops.conv_nhwc_bf16_ex(x, w, 1, 1, w.shape[1], bias=b, act=act, residual=block_in if res else None,
+                                                  in_padded=True, out_padded=True)
+                    else:
+                        x = ops.conv_nhwc_bf16(x, w, 1, 1, bias=b, act=act, residual=block_in if res else None)
                     if ends:
                         block_in = x
                 elif kind == "dw":

@@ -327,7 +327,37 @@ def conv_nhwc_bf16(x, w, ksize, stride, bias=None, act=None, residual=None, out=
     return out
 
 
-def stem_conv(x, w, bias, out=None):
+def conv_nhwc_bf16_ex(x, w, ksize, stride, cin, bias=None, act=None, residual=None, out=None, in_padded=False, out_padded=False):
+    """conv_nhwc_bf16 on "padded-flat" tensors: x [n,h(+2),w(+2),cin], out/residual [n,ho(+2),wo(+2),cout] (see
+    ewvit_conv_nhwc_bf16_ex in include/ewvit.h; stride-2 convs with out_padded write the interior of ``out`` only)."""
+    _check_bf16(x, "x", 4)
+    _check_bf16(w, "w")
+    n = x.shape[0]
+    h, wd = (x.shape[1] - 2, x.shape[2] - 2) if in_padded else (x.shape[1], x.shape[2])
+    if x.shape[3] != cin:
+        raise EwvitError("conv_nhwc_bf16_ex: channel mismatch")
+    cout = w.shape[0]
+    ho, wo = (h - 1) // stride + 1, (wd - 1) // stride + 1
+    oshape = (n, ho + 2, wo + 2, cout) if out_padded else (n, ho, wo, cout)
+    if out is None:
+        if out_padded and not (ksize == 1 or (stride == 1 and in_padded)):
+            raise EwvitError("conv_nhwc_bf16_ex: this conv writes the interior only; pass a zero-bordered out tensor")
+        out = torch.empty(oshape, dtype=torch.bfloat16, device=x.device)
+    elif tuple(out.shape) != oshape or out.dtype != torch.bfloat16 or not out.is_contiguous():
+        raise EwvitError("conv_nhwc_bf16_ex: bad out tensor")
+    if residual is not None:
+        _check_bf16(residual, "residual")
+        if residual.numel() != out.numel():
+            raise EwvitError("conv_nhwc_bf16_ex: residual must match the output")
+    bias = _f32_or_none(bias, "bias", cout)
+    with torch.cuda.device(x.device):
+        check(load().ewvit_conv_nhwc_bf16_ex(x.data_ptr(), w.data_ptr(), n, h, wd, cin, cout, ksize, stride, _ptr(bias), ACT_BB[act],
+                                             _ptr(residual), out.data_ptr(), int(in_padded), int(out_padded), _stream()),
+              "ewvit_conv_nhwc_bf16_ex")
+    return out
+
+
+def stem_conv(x, w, bias, out=None, out_padded=False):
     """fp32 NCHW frames [n,3,h,w] -> bf16 NHWC [n,h/2,w/2,cout]: conv3x3 s2 + bias + SiLU."""
     _check_f32(x, "x")
     _check_f32(w, "w")
@@ -336,11 +366,19 @@ def stem_conv(x, w, bias, out=None):
     if c != 3 or w.numel() != cout * 27:
         raise EwvitError("stem_conv: expects 3 input channels and [cout,3,3,3] weights")
     bias = _f32_or_none(bias, "bias", cout)
-    if out is None:
-        out = torch.empty((n, (h - 1) // 2 + 1, (wd - 1) // 2 + 1, cout), dtype=torch.bfloat16, device=x.device)
+    ho, wo = (h - 1) // 2 + 1, (wd - 1) // 2 + 1
+    if out_padded:
+        if out is None:
+            out = torch.zeros((n, ho + 2, wo + 2, cout), dtype=torch.bfloat16, device=x.device)
+        elif tuple(out.shape) != (n, ho + 2, wo + 2, cout) or out.dtype != torch.bfloat16 or not out.is_contiguous():
+            raise EwvitError("stem_conv: bad padded out tensor")
+        fn = load().ewvit_stem_conv_padded_fwd
+    else:
+        if out is None:
+            out = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
+        fn = load().ewvit_stem_conv_fwd
     with torch.cuda.device(x.device):
-        check(load().ewvit_stem_conv_fwd(x.data_ptr(), n, h, wd, w.data_ptr(), bias.data_ptr(), cout, out.data_ptr(),
-                                         _stream()), "ewvit_stem_conv_fwd")
+        check(fn(x.data_ptr(), n, h, wd, w.data_ptr(), bias.data_ptr(), cout, out.data_ptr(), _stream()), "ewvit_stem_conv_fwd")
     return out
 
 

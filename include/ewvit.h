@@ -225,10 +225,23 @@ EWVIT_API int ewvit_video_head_fwd(const float *fused, const float *space, const
 EWVIT_API int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, int wd, int cin, int cout, int ksize,
                                    int stride, const float *bias, int act, const void *residual, void *y, void *stream);
 
+/* The same convolution on "padded-flat" tensors [n, h+2, wd+2, c] (one-pixel zero border around every image):
+ *   in_padded / out_padded say which of x / (y, residual) use that layout.  Padded outputs: 1x1 convs and the stride-1
+ *   small-channel 3x3 convs write the border as zeros; the stride-2 small-channel 3x3 convs write the interior only (the
+ *   caller zeroes the buffer once).  1x1 convs need in_padded == out_padded.  A 3x3 stride-1 conv with cin < 64 on padded
+ *   input AND output takes the "overlapping window" path: its weights are w [cout, 3*nsub*64] bf16 with
+ *   nsub = ceil(3*cin/64) and k = dy*(nsub*64) + dx*cin + c (zero elsewhere); every other case uses the layouts above. */
+EWVIT_API int ewvit_conv_nhwc_bf16_ex(const void *x, const void *w, int n, int h, int wd, int cin, int cout, int ksize,
+                                      int stride, const float *bias, int act, const void *residual, void *y, int in_padded,
+                                      int out_padded, void *stream);
+
 /* Stem: Conv2d(3 -> cout, 3x3, stride 2, pad 1) + bias + SiLU straight from the fp32 NCHW frames (also the
  * fp32 -> bf16 / NCHW -> NHWC conversion).  x [n,3,h,wd] fp32, w [cout,3,3,3] fp32, y [n,ho,wo,cout] bf16. */
 EWVIT_API int ewvit_stem_conv_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
                                   void *y, void *stream);
+/* Same, writing the interior of a padded-flat output y [n, ho+2, wo+2, cout] (the caller zeroes the border once). */
+EWVIT_API int ewvit_stem_conv_padded_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
+                                         void *y, void *stream);
 
 /* Depthwise 3x3 (pad 1, stride 1|2) + bias + SiLU, plus the squeeze of the SE block: pooled[n, c] = spatial mean of
  * the stored result (NULL to skip).  x [n,h,wd,c] bf16, w [9, c] fp32 (tap-major), y [n,ho,wo,c] bf16; c % 64 == 0. */

@@ -73,6 +73,78 @@ def test_stem(ops):
     _close(got.permute(0, 3, 1, 2), ref, tol=1e-4)
 
 
+def _pad_nhwc(x_nchw):
+    """NCHW -> padded-flat NHWC [n, h+2, w+2, c] with a zero border."""
+    return F.pad(_nhwc(x_nchw), (0, 0, 1, 1, 1, 1)).contiguous()
+
+
+def _check_padded(got, ref, tol=2e-3):
+    """interior == ref, border == 0"""
+    _close(got[:, 1:-1, 1:-1].permute(0, 3, 1, 2), ref, tol=tol)
+    g = got.float()
+    assert float(g[:, 0].abs().max()) == 0 and float(g[:, -1].abs().max()) == 0
+    assert float(g[:, :, 0].abs().max()) == 0 and float(g[:, :, -1].abs().max()) == 0
+
+
+@pytest.mark.parametrize("cin,cout,res,hw", [(24, 24, True, (112, 112)), (48, 192, False, (56, 56)), (16, 64, False, (20, 12)),
+                                            (40, 264, False, (9, 30))])
+def test_conv3x3_window_path(ops, cin, cout, res, hw):
+    """overlapping-window TMA path (padded-flat in and out, cin < 64, stride 1) == F.conv2d"""
+    from ewvit import engine
+    n, (h, w) = 2, hw
+    x = seeded_randn((n, cin, h, w), 31).bfloat16()
+    wt = (seeded_randn((cout, cin, 3, 3), 32) * (9 * cin) ** -0.5).bfloat16()
+    b = seeded_randn((cout,), 33)
+    ref = F.silu(F.conv2d(x.float(), wt.float(), b, padding=1))
+    if res:
+        ref = ref + x.float()
+    xp = _pad_nhwc(x).cuda()
+    got = ops.conv_nhwc_bf16_ex(xp, engine._w3x3_window_packed(wt.float()).cuda(), 3, 1, cin, bias=b.cuda(), act="silu",
+                                residual=xp if res else None, in_padded=True, out_padded=True)
+    assert got.shape == (n, h + 2, w + 2, cout)
+    _check_padded(got.cpu(), ref)
+
+
+def test_conv1x1_padded_layout(ops):
+    n, cin, cout, h, w = 3, 96, 48, 14, 10
+    x = seeded_randn((n, cin, h, w), 34).bfloat16()
+    wt = (seeded_randn((cout, cin, 1, 1), 35) * cin ** -0.5).bfloat16()
+    b = seeded_randn((cout,), 36) + 1.0       # a non-zero bias would leak into the border without the masking
+    r = seeded_randn((n, cout, h, w), 37).bfloat16()
+    ref = F.conv2d(x.float(), wt.float(), b) + r.float()
+    got = ops.conv_nhwc_bf16_ex(_pad_nhwc(x).cuda(), wt.flatten(1).contiguous().cuda(), 1, 1, cin, bias=b.cuda(),
+                                residual=_pad_nhwc(r).cuda(), in_padded=True, out_padded=True)
+    _check_padded(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("cin,cout,out_padded,hw", [(24, 96, True, (112, 112)), (48, 192, False, (56, 56)), (24, 96, True, (20, 12))])
+def test_conv3x3_stride2_from_padded_input(ops, cin, cout, out_padded, hw):
+    from ewvit import engine
+    n, (h, w) = 2, hw
+    x = seeded_randn((n, cin, h, w), 38).bfloat16()
+    wt = (seeded_randn((cout, cin, 3, 3), 39) * (9 * cin) ** -0.5).bfloat16()
+    b = seeded_randn((cout,), 40)
+    ref = F.silu(F.conv2d(x.float(), wt.float(), b, stride=2, padding=1))
+    ho, wo = ref.shape[2:]
+    out = torch.zeros((n, ho + 2, wo + 2, cout), dtype=torch.bfloat16, device="cuda") if out_padded else None
+    got = ops.conv_nhwc_bf16_ex(_pad_nhwc(x).cuda(), engine._w3x3_tapmajor_padded(wt.float()).cuda(), 3, 2, cin, bias=b.cuda(),
+                                act="silu", out=out, in_padded=True, out_padded=out_padded)
+    if out_padded:
+        _check_padded(got.cpu(), ref)
+    else:
+        _close(got.permute(0, 3, 1, 2), ref)
+
+
+def test_stem_padded(ops):
+    x = seeded_randn((2, 3, 224, 224), 8)
+    wt = seeded_randn((24, 3, 3, 3), 9) * 27 ** -0.5
+    b = seeded_randn((24,), 10)
+    ref = F.silu(F.conv2d(x, wt, b, stride=2, padding=1))
+    got = ops.stem_conv(x.cuda(), wt.cuda().contiguous(), b.cuda(), out_padded=True)
+    assert got.shape == (2, 114, 114, 24)
+    _check_padded(got.cpu(), ref, tol=1e-4)
+
+
 @pytest.mark.parametrize("c,stride,hw", [(256, 2, (28, 28)), (960, 1, (14, 14)), (1536, 1, (7, 7)), (960, 2, (14, 14)), (64, 1, (5, 9))])
 def test_depthwise_and_squeeze(ops, c, stride, hw):
     n, (h, w) = 3, hw
