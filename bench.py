@@ -153,6 +153,21 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def load_ncu_traffic(key, frames):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the named kernel from the latest committed `ncu --set full` capture
+    (profiles/<tag>_traffic.json, written by tools/make_profile_md.py), scaled to this run's frames per launch; None if
+    there is no capture."""
+    import glob
+    files = sorted(glob.glob(os.path.join(REPO, "profiles", "*_traffic.json")))
+    if not files:
+        return None
+    try:
+        rec = json.load(open(files[-1])).get(key)
+        return None if rec is None else rec["dram_bytes"] * frames / rec["frames"]
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -299,7 +314,9 @@ def main():
     achieved = conv_flops / (ms_conv / 1e3) / 1e12
     roofline = {"kernel": "gemm_tc_kernel<EPI_CONV> multiscale_fusion 384->128 @112x112 (mwt.py:68-72)", "bound": "tensor",
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": load_ncu_traffic("multiscale_512_frames", n_frames),
+                "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/*_traffic.json)",
+                "algorithmic_bytes_per_launch": n_frames * 114 * 114 * (384 + 128) * 2 + 128 * 3456 * 2,
                 "ms_per_launch": ms_conv, "flops_per_launch": conv_flops,
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)"}
     dwt_bytes_pipe = n_frames * 3 * SIDE * SIDE * 4 * 2              # frames read once + HF1-3 written once (LL never leaves the SM)
