@@ -230,6 +230,165 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __grid_constant
     }
 }
 
+// ---- 3x3 / stride 1 / pad 1 convolution with 24 input and 24 output channels + bias + SiLU (+ residual = the input):
+//      the two stage-1 FusedMBConv blocks of EfficientNetV2-S at 112x112.  With N = 24 a 128-row tcgen05 tile is all
+//      fixed cost (the assembled-A path spent ~2600 cycles per 128x24 tile building operands), so these layers use
+//      warp-level mma.sync.m16n8k16 on a direct-convolution tile instead: a CTA owns 16x16 output pixels, the 18x18x24
+//      input halo sits in shared memory (80-byte pixel pitch: conflict-free ldmatrix rows), and an A fragment of tap
+//      (dy, dx) is simply ldmatrix on the pixel rows shifted by that tap -- no im2col copy exists anywhere.  K = 216
+//      dense (27 chunks of 8 channels, chunk 27 reads zeros), weights [24][K] stay in shared memory.
+constexpr int kC24 = 24;
+constexpr int kC24Tile = 16;
+constexpr int kC24Halo = kC24Tile + 2;                 // 18
+constexpr int kC24Pitch = 80;                           // bytes per halo pixel (24 channels = 48 bytes + padding)
+constexpr int kC24HaloBytes = kC24Halo * kC24Halo * kC24Pitch;   // 25920
+constexpr int kC24KSteps = 14;                          // 28 chunks of 8 channels (27 real)
+constexpr int kC24WPitch = 464;                         // bytes per weight row: 224 elements + padding (conflict-free ldmatrix)
+constexpr int kC24Smem = 2 * kC24HaloBytes + kC24 * kC24WPitch + 128 /*zeros*/ + 128;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t &r0, uint32_t &r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 3) conv3x3_c24_kernel(const __nv_bfloat16 *__restrict__ x, const __nv_bfloat16 *__restrict__ w, int wk,
+                                                             const float *__restrict__ bias, __nv_bfloat16 *__restrict__ y, int n, int h,
+                                                             int wd, int residual) {
+    extern __shared__ __align__(128) unsigned char c24_smem[];
+    const uint32_t s_halo = ewvit::smem_u32(c24_smem);                          // [2][18*18][80 B]
+    const uint32_t s_w = s_halo + 2 * kC24HaloBytes;                            // [24][464 B]
+    const uint32_t s_zero = s_w + kC24 * kC24WPitch;                            // 128 B of zeros
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_x = (wd + kC24Tile - 1) / kC24Tile, tiles_y = (h + kC24Tile - 1) / kC24Tile;
+    const long long tiles = (long long)n * tiles_y * tiles_x;
+
+    // weights (K-major rows, dense k = tap*24 + c) and the zero block
+    for (int i = tid; i < kC24 * 28; i += 256) {
+        const int row = i / 28, q = i - row * 28;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (q * 8 < wk) v = __ldg(reinterpret_cast<const uint4 *>(w + (long long)row * wk + q * 8));
+        if (q == 27) v = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(s_w + row * kC24WPitch + q * 16), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    if (tid < 8) asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(s_zero + tid * 16), "r"(0u) : "memory");
+
+    auto stage = [&](long long t, int buf) {       // halo of tile t -> buffer buf (out-of-image pixels zero-filled)
+        const int tx = (int)(t % tiles_x);
+        const long long t2 = t / tiles_x;
+        const int ty = (int)(t2 % tiles_y);
+        const long long img = t2 / tiles_y;
+        const int y0 = ty * kC24Tile - 1, x0 = tx * kC24Tile - 1;
+        const __nv_bfloat16 *src = x + img * h * wd * kC24;
+        const uint32_t dst = s_halo + buf * kC24HaloBytes;
+        for (int i = tid; i < kC24Halo * kC24Halo * 3; i += 256) {
+            const int px = i / 3, j = i - px * 3;
+            const int hy = px / kC24Halo, hx = px - hy * kC24Halo;
+            const int gy = y0 + hy, gx = x0 + hx;
+            const bool in = gy >= 0 && gy < h && gx >= 0 && gx < wd;
+            const __nv_bfloat16 *g = src + ((long long)(in ? gy : 0) * wd + (in ? gx : 0)) * kC24 + j * 8;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + px * kC24Pitch + j * 16), "l"(g), "r"(in ? 16 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // per-lane ldmatrix geometry.  A: lane -> (pixel row of the m16 tile, k half); B: lane -> (output channel, k half)
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
+    const int b_n = ((lane >> 4) << 3) + (lane & 7), b_kh = (lane >> 3) & 1;
+    uint32_t a_off[kC24KSteps];                      // byte offset of this lane's chunk within the halo, relative to the tile pixel
+#pragma unroll
+    for (int s2 = 0; s2 < kC24KSteps; ++s2) {
+        const int q = 2 * s2 + a_kh;
+        const int tap = q / 3, part = q - tap * 3;
+        const int dy = tap / 3, dx = tap - dy * 3;
+        a_off[s2] = q < 27 ? (uint32_t)((dy * kC24Halo + dx) * kC24Pitch + part * 16) : 0xFFFFFFFFu;
+    }
+    float bv[3][2];
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+        bv[nt][0] = bias[nt * 8 + 2 * (lane & 3)];
+        bv[nt][1] = bias[nt * 8 + 2 * (lane & 3) + 1];
+    }
+
+    long long t = blockIdx.x;
+    if (t < tiles) stage(t, 0);
+    int buf = 0;
+    for (; t < tiles; t += gridDim.x, buf ^= 1) {
+        const long long tn = t + gridDim.x;
+        if (tn < tiles) {
+            stage(tn, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int tx = (int)(t % tiles_x);
+        const long long t2 = t / tiles_x;
+        const int ty = (int)(t2 % tiles_y);
+        const long long img = t2 / tiles_y;
+        const uint32_t halo = s_halo + buf * kC24HaloBytes;
+        // warp -> output rows 2*warp, 2*warp + 1 of the tile (two m16 tiles of 16 pixels each)
+        float acc[2][3][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[m][nt][e] = 0.f;
+        const uint32_t a_base0 = halo + ((2 * warp) * kC24Halo + a_row) * kC24Pitch;          // pixel (row 2w, col a_row) + tap offset
+        const uint32_t a_base1 = a_base0 + kC24Halo * kC24Pitch;
+        const uint32_t b_base = s_w + b_n * kC24WPitch + b_kh * 16;
+#pragma unroll
+        for (int s2 = 0; s2 < kC24KSteps; ++s2) {
+            uint32_t a0[4], a1[4], b01[4], b2[2];
+            const bool zero = a_off[s2] == 0xFFFFFFFFu;
+            ldsm_x4(zero ? s_zero : a_base0 + a_off[s2], a0[0], a0[1], a0[2], a0[3]);
+            ldsm_x4(zero ? s_zero : a_base1 + a_off[s2], a1[0], a1[1], a1[2], a1[3]);
+            ldsm_x4(b_base + s2 * 32, b01[0], b01[1], b01[2], b01[3]);                        // output channels 0..15
+            ldsm_x2(s_w + (16 + (lane & 7)) * kC24WPitch + ((lane >> 3) & 1) * 16 + s2 * 32, b2[0], b2[1]);   // 16..23
+            mma_bf16_16816(acc[0][0], a0[0], a0[1], a0[2], a0[3], b01[0], b01[1]);
+            mma_bf16_16816(acc[0][1], a0[0], a0[1], a0[2], a0[3], b01[2], b01[3]);
+            mma_bf16_16816(acc[0][2], a0[0], a0[1], a0[2], a0[3], b2[0], b2[1]);
+            mma_bf16_16816(acc[1][0], a1[0], a1[1], a1[2], a1[3], b01[0], b01[1]);
+            mma_bf16_16816(acc[1][1], a1[0], a1[1], a1[2], a1[3], b01[2], b01[3]);
+            mma_bf16_16816(acc[1][2], a1[0], a1[1], a1[2], a1[3], b2[0], b2[1]);
+        }
+        // epilogue: bias + SiLU (+ the input pixel, read back from the halo) -> bf16
+        const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int oy = ty * kC24Tile + 2 * warp + m;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int px = g + 8 * hh, ox = tx * kC24Tile + px;
+                if (oy < h && ox < wd) {
+                    __nv_bfloat16 *dst = y + ((img * h + oy) * wd + ox) * kC24 + 2 * tq;
+                    const uint32_t res_addr = halo + ((2 * warp + m + 1) * kC24Halo + px + 1) * kC24Pitch + 4 * tq;
+#pragma unroll
+                    for (int nt = 0; nt < 3; ++nt) {
+                        float v0 = silu(acc[m][nt][2 * hh] + bv[nt][0]), v1 = silu(acc[m][nt][2 * hh + 1] + bv[nt][1]);
+                        if (residual) {
+                            uint32_t rv;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rv) : "r"(res_addr + nt * 16) : "memory");
+                            v0 += __uint_as_float(rv << 16);
+                            v1 += __uint_as_float(rv & 0xffff0000u);
+                        }
+                        const __nv_bfloat162 o = __floats2bfloat162_rn(v0, v1);
+                        *reinterpret_cast<uint32_t *>(dst + nt * 8) = *reinterpret_cast<const uint32_t *>(&o);
+                    }
+                }
+            }
+        }
+        __syncthreads();      // everyone is done with this halo buffer before the next stage() overwrites it
+    }
+}
+
 // ---- squeeze-excitation gate: gate[n, c] = sigmoid(W2 * silu(W1 * pooled[n] + b1) + b2).
 //      One CTA serves kSeF frames, so each weight matrix (up to 0.4 MB at c = 1536) is pulled from L2 once per kSeF
 //      frames; both layers read the weights as float4 with several independent loads in flight per thread (the
@@ -427,6 +586,32 @@ extern "C" int ewvit_dwconv3x3_nhwc_bf16(const void *x, const float *w, const fl
     }
     if (stride == 1) return launch_dw<32, 1>(tm, w, bias, y, pooled, n, h, wd, ho, wo, c, fb, stage_bytes, smem, (unsigned)grid, st);
     return launch_dw<32, 2>(tm, w, bias, y, pooled, n, h, wd, ho, wo, c, fb, stage_bytes, smem, (unsigned)grid, st);
+}
+
+extern "C" int ewvit_conv3x3_c24_fwd(const void *x, const void *w, int wk, const float *bias, int n, int h, int wd, int residual, void *y,
+                                     void *stream) {
+    EWVIT_REQUIRE(n >= 0 && h > 0 && wd > 0, EWVIT_ERR_INVALID_ARG, "ewvit_conv3x3_c24_fwd: bad sizes");
+    if (n == 0) return EWVIT_OK;
+    EWVIT_REQUIRE(x && w && bias && y && ewvit_aligned16(x) && ewvit_aligned16(w) && ewvit_aligned16(y), EWVIT_ERR_INVALID_ARG,
+                  "ewvit_conv3x3_c24_fwd: NULL or misaligned pointer");
+    EWVIT_REQUIRE(wk >= 216 && wk % 8 == 0, EWVIT_ERR_INVALID_ARG, "ewvit_conv3x3_c24_fwd: weight rows must hold >= 216 elements (got %d)", wk);
+    int rc = ewvit_check_device();
+    if (rc != EWVIT_OK) return rc;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    EWVIT_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(conv3x3_c24_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC24Smem));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const long long tiles = (long long)n * ((h + kC24Tile - 1) / kC24Tile) * ((wd + kC24Tile - 1) / kC24Tile);
+    long long grid = 3LL * ewvit_num_sms();
+    if (grid > tiles) grid = tiles;
+    conv3x3_c24_kernel<<<(unsigned)grid, 256, kC24Smem, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16 *>(x),
+                                                                               static_cast<const __nv_bfloat16 *>(w), wk, bias,
+                                                                               static_cast<__nv_bfloat16 *>(y), n, h, wd, residual ? 1 : 0);
+    EWVIT_LAUNCH_OK();
+    return EWVIT_OK;
 }
 
 extern "C" int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const float *w1, const float *b1, const float *w2t,

@@ -39,6 +39,7 @@ SIGNATURES = {
     "ewvit_dama_wpack_floats": (c_int64, [c_int, c_int]),
     "ewvit_dama_tail_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, P, c_float, P, P, P, P]),
     "ewvit_conv_nhwc_bf16": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, P]),
+    "ewvit_conv3x3_c24_fwd": (c_int, [P, P, c_int, P, c_int, c_int, c_int, c_int, P, P]),
     "ewvit_stem_conv_fwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P]),
     "ewvit_stem_conv_padded_fwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P]),
     "ewvit_conv_nhwc_bf16_ex": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, c_int, c_int, P]),
@@ -46,6 +47,7 @@ SIGNATURES = {
     "ewvit_se_apply_nhwc_bf16": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     "ewvit_se_gate_fwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P]),
     "ewvit_conv1x1_gated_nhwc_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, c_int, P, P, P]),
+    "ewvit_mwt_head_mma_fwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "ewvit_mwt_upsample_fwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "ewvit_mwt_head_conv_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P]),
     "ewvit_debug_set_trace": (c_int, [P]),

@@ -120,7 +120,7 @@ class MwtRunner:
         self.head_scale64[:54] = self.head_scale
         self.head_shift64[:54] = self.head_shift
         import os
-        self.head_tc = os.environ.get("EWVIT_HEAD", "tc") != "simt"
+        self.head_mode = os.environ.get("EWVIT_HEAD", "tc")        # tc (default: upsample + tcgen05 conv) | mma (one warp-MMA kernel, same speed) | simt (fp32 CUDA cores)
         self.fus_w = _conv_w_tapmajor(sd["hf_conv.fusion.0.weight"], 64)
         self.fus_scale, self.fus_shift = _fold_bn(sd, "hf_conv.fusion.0.", "hf_conv.fusion.1.")
         self.ms_w = _conv_w_tapmajor(sd["multiscale_fusion.0.weight"])
@@ -167,11 +167,11 @@ class MwtRunner:
         for lvl in range(3):
             with stage("mwt.head"):
                 hfl = hf[lvl].view(n, 9, h >> (lvl + 1), w >> (lvl + 1))
-                if self.head_tc:
+                if self.head_mode == "tc":
                     ops.mwt_upsample(hfl, ws["up"], h1, w1)
                     ops.mwt_head_conv(ws["up"], self.head_wbd, self.head_scale64, self.head_shift64, ws["head"], h1, w1)
                 else:
-                    ops.mwt_head(hfl, self.head_w, self.head_scale, self.head_shift, ws["head"], h1, w1)
+                    ops.mwt_head(hfl, self.head_w, self.head_scale, self.head_shift, ws["head"], h1, w1, mma=self.head_mode == "mma")
             with stage("mwt.hf_fusion"):
                 ops.conv3x3_bf16(ws["head"], self.fus_w, n, h1, w1, 1, True, self.fus_scale, self.fus_shift, True,
                                  ws["cat"], lvl * d, True)
@@ -257,6 +257,7 @@ class NativeEffNetV2:
         self.device = dev
         self.ops = []
         self.fuse_se = os.environ.get("EWVIT_SE_FUSED", "1") == "1"
+        self.c24 = os.environ.get("EWVIT_C24_DIRECT", "1") == "1"
         self.win_w, self.cin3 = {}, {}      # op index -> window-packed weights / input channels of the 3x3 convs
         self._padbuf = {}
         mods = list(features)
@@ -384,6 +385,9 @@ class NativeEffNetV2:
                             out = self._zero_bordered(i, (n, (hp - 1) // stride + 3, (wp - 1) // stride + 3, w.shape[0]))
                         x = ops.conv_nhwc_bf16_ex(x, self.win_w[i] if window else w, 3, stride, self.cin3[i], bias=b, act=act,
                                                   residual=block_in if res else None, out=out, in_padded=in_p, out_padded=out_p)
+                    elif self.cin3[i] == 24 and w.shape[0] == 24 and stride == 1 and act == "silu" and self.c24 \
+                            and (not res or block_in is x):
+                        x = ops.conv3x3_c24(x, w, b, residual=res)       # direct conv on warp-level MMAs (N = 24)
                     else:
                         x = ops.conv_nhwc_bf16(x, w, 3, stride, bias=b, act=act, residual=block_in if res else None)
                     if ends:

@@ -147,8 +147,9 @@ def _check_f32(t, name):
         raise EwvitError(f"{name} must be a contiguous fp32 CUDA tensor")
 
 
-def mwt_head(hf, w, scale, shift, y, hout, wout):
-    """hf [n,9,hin,win] fp32 -> y [n,hout+2,wout+2,64] bf16 (interior written). See include/ewvit.h."""
+def mwt_head(hf, w, scale, shift, y, hout, wout, mma=False):
+    """hf [n,9,hin,win] fp32 -> y [n,hout+2,wout+2,64] bf16 (interior written). See include/ewvit.h.
+    mma=True: the warp-level tensor-core kernel (bf16 operands), else the fp32 CUDA-core kernel."""
     for t, nm in ((hf, "hf"), (w, "w"), (scale, "scale"), (shift, "shift")):
         _check_f32(t, nm)
     _check_bf16(y, "y")
@@ -157,9 +158,10 @@ def mwt_head(hf, w, scale, shift, y, hout, wout):
         raise EwvitError("mwt_head: expects 9 high-frequency channels (in_channels=3) and 3x18x27 weights")
     if y.numel() != n * (hout + 2) * (wout + 2) * 64:
         raise EwvitError("mwt_head: bad y size")
+    fn = load().ewvit_mwt_head_mma_fwd if mma else load().ewvit_mwt_head_fwd
     with torch.cuda.device(hf.device):
-        check(load().ewvit_mwt_head_fwd(hf.data_ptr(), n, hin, win, hout, wout, w.data_ptr(), scale.data_ptr(),
-                                        shift.data_ptr(), y.data_ptr(), _stream()), "ewvit_mwt_head_fwd")
+        check(fn(hf.data_ptr(), n, hin, win, hout, wout, w.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), _stream()),
+              "ewvit_mwt_head_mma_fwd" if mma else "ewvit_mwt_head_fwd")
     return y
 
 
@@ -354,6 +356,22 @@ def conv_nhwc_bf16_ex(x, w, ksize, stride, cin, bias=None, act=None, residual=No
         check(load().ewvit_conv_nhwc_bf16_ex(x.data_ptr(), w.data_ptr(), n, h, wd, cin, cout, ksize, stride, _ptr(bias), ACT_BB[act],
                                              _ptr(residual), out.data_ptr(), int(in_padded), int(out_padded), _stream()),
               "ewvit_conv_nhwc_bf16_ex")
+    return out
+
+
+def conv3x3_c24(x, w, bias, residual=False, out=None):
+    """3x3/s1/p1 conv 24 -> 24 + bias + SiLU (+ x) on NHWC bf16 (ewvit_conv3x3_c24_fwd); w [24, >=216] dense tap-major."""
+    _check_bf16(x, "x", 4)
+    _check_bf16(w, "w", 2)
+    n, h, wd, c = x.shape
+    if c != 24 or w.shape[0] != 24 or w.shape[1] < 216:
+        raise EwvitError("conv3x3_c24: needs 24 input/output channels and [24, >=216] weights")
+    bias = _f32_or_none(bias, "bias", 24)
+    if out is None:
+        out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(load().ewvit_conv3x3_c24_fwd(x.data_ptr(), w.data_ptr(), w.shape[1], bias.data_ptr(), n, h, wd, int(bool(residual)),
+                                           out.data_ptr(), _stream()), "ewvit_conv3x3_c24_fwd")
     return out
 
 

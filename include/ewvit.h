@@ -139,6 +139,13 @@ EWVIT_API int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, int
 EWVIT_API int ewvit_mwt_head_fwd(const float *hf, int n, int hin, int win, int hout, int wout, const float *w,
                                  const float *scale, const float *shift, void *y, void *stream);
 
+/* The same head (network/mwt.py:77-86) as ONE kernel on warp-level tensor-core MMAs: the bilinear upsample is evaluated
+ * straight into a shared-memory halo and the block-diagonal 9 -> 54 conv runs as a direct convolution (ldmatrix on
+ * tap-shifted halo pixels, mma.sync.m16n8k16), so the 16-channel intermediate never exists in HBM.  Same arguments and
+ * output contract as ewvit_mwt_head_fwd (operands rounded to bf16, fp32 accumulation). */
+EWVIT_API int ewvit_mwt_head_mma_fwd(const float *hf, int n, int hin, int win, int hout, int wout, const float *w,
+                                     const float *scale, const float *shift, void *y, void *stream);
+
 /* Tensor-core variant of the high-frequency head (same reference lines, network/mwt.py:77-86), in two steps:
  *   1. ewvit_mwt_upsample_fwd: hf [n, 9, hin, win] fp32 -> bilinear upsample (identity when hin == hout) ->
  *      up [n, hout+2, wout+2, 16] bf16 padded-flat NHWC (channels 9..15 zero).  Only interior pixels are written: the
@@ -234,6 +241,13 @@ EWVIT_API int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, i
 EWVIT_API int ewvit_conv_nhwc_bf16_ex(const void *x, const void *w, int n, int h, int wd, int cin, int cout, int ksize,
                                       int stride, const float *bias, int act, const void *residual, void *y, int in_padded,
                                       int out_padded, void *stream);
+
+/* 3x3 / stride 1 / pad 1 convolution with exactly 24 input and 24 output channels + bias + SiLU (+ residual = x):
+ * the stage-1 FusedMBConv blocks of EfficientNetV2-S.  Direct convolution on warp-level tensor-core MMAs (a 128-row
+ * tcgen05 tile is all overhead at N = 24).  x, y [n, h, wd, 24] bf16; w [24, wk] bf16 in the dense tap-major layout of
+ * ewvit_conv_nhwc_bf16 (k = (ky*3+kx)*24 + c, wk >= 216 elements per row); bias [24] fp32. */
+EWVIT_API int ewvit_conv3x3_c24_fwd(const void *x, const void *w, int wk, const float *bias, int n, int h, int wd, int residual,
+                                    void *y, void *stream);
 
 /* Stem: Conv2d(3 -> cout, 3x3, stride 2, pad 1) + bias + SiLU straight from the fp32 NCHW frames (also the
  * fp32 -> bf16 / NCHW -> NHWC conversion).  x [n,3,h,wd] fp32, w [cout,3,3,3] fp32, y [n,ho,wo,cout] bf16. */

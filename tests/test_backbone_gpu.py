@@ -63,6 +63,21 @@ def test_conv3x3_small_channels(ops, cin, cout, stride, res, hw):
     _close(got.permute(0, 3, 1, 2), ref)
 
 
+@pytest.mark.parametrize("res,hw", [(True, (112, 112)), (False, (20, 12)), (True, (17, 33))])
+def test_conv3x3_c24_direct(ops, res, hw):
+    """warp-level-MMA direct conv of the 24 -> 24 stage-1 blocks == F.conv2d + SiLU (+ x)"""
+    from ewvit import engine
+    n, (h, w) = 3, hw
+    x = seeded_randn((n, 24, h, w), 41).bfloat16()
+    wt = (seeded_randn((24, 24, 3, 3), 42) * (9 * 24) ** -0.5).bfloat16()
+    b = seeded_randn((24,), 43)
+    ref = F.silu(F.conv2d(x.float(), wt.float(), b, padding=1))
+    if res:
+        ref = ref + x.float()
+    got = ops.conv3x3_c24(_nhwc(x).cuda(), engine._w3x3_tapmajor_padded(wt.float()).cuda(), b.cuda(), residual=res)
+    _close(got.permute(0, 3, 1, 2), ref)
+
+
 def test_stem(ops):
     x = seeded_randn((3, 3, 224, 224), 8)
     wt = seeded_randn((24, 3, 3, 3), 9) * 27 ** -0.5

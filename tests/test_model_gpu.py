@@ -68,6 +68,13 @@ def test_mwt_head_kernel(dama_sd, sd_cuda, frames):
         check(f"mwt_head level {lvl + 1}", got[:, 1:-1, 1:-1, :54].permute(0, 3, 1, 2), ref, 1e-2)
         assert float(got[:, 1:-1, 1:-1, 54:].abs().max()) == 0.0
         assert float(got[:, 0].abs().max()) == 0.0 and float(got[:, :, -1].abs().max()) == 0.0
+        # warp-level-MMA variant (one kernel, upsample fused): same contract
+        y3 = torch.zeros((2, 114, 114, 64), dtype=torch.bfloat16, device="cuda")
+        ops.mwt_head(hf.view(2, 9, hf.shape[-2], hf.shape[-1]), run.head_w, run.head_scale, run.head_shift, y3, 112, 112, mma=True)
+        got3 = y3.float().cpu()
+        check(f"mwt_head mma level {lvl + 1}", got3[:, 1:-1, 1:-1, :54].permute(0, 3, 1, 2), ref, 2e-2)
+        assert float(got3[:, 1:-1, 1:-1, 54:].abs().max()) == 0.0
+        assert float(got3[:, 0].abs().max()) == 0.0 and float(got3[:, :, -1].abs().max()) == 0.0
         # tensor-core variant: bf16 upsampled planes -> block-diagonal conv through TMA's overlapping-window map
         up = torch.zeros((2, 114, 114, 16), dtype=torch.bfloat16, device="cuda")
         y2 = torch.full((2, 114, 114, 64), 7.0, dtype=torch.bfloat16, device="cuda")     # borders must come out as zeros
