@@ -147,12 +147,24 @@ __device__ __forceinline__ void tma_store_4d(const void *tmap, uint32_t src, int
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
+// work item w of this CTA -> (row tile, column tile, K split); always true for the m-fastest order
+__device__ __forceinline__ bool decode_tile(const GemmParams &p, int w, int &m_t, int &n_t, int &sp) {
+    m_t = w % p.tiles_m;            // m fastest: a CTA keeps its column tile (and its staged bias) for many consecutive tiles
+    const int wn = w / p.tiles_m;
+    n_t = wn % p.tiles_n;
+    sp = wn / p.tiles_n;
+    return true;
+}
+
 #define EWVIT_TRACE(role, tile, k)                                                                  \
     do {                                                                                            \
         if (p.trace && blockIdx.x == 0 && (tile) < 64) p.trace[((role) * 64 + (tile)) * 4 + (k)] = clock64(); \
     } while (0)
 
-template <int kEpi, bool kBuilder, int kBN>
+// kFast (EPI_BB only): 0 = generic epilogue (runtime activation / residual switches), 1 = SiLU on pre-halved operands
+// without residual, 2 = no activation (+ optional bf16 residual).  The specialised bodies are ONE basic block per 32-column chunk
+// (32 independent values per lane for the scheduler) -- the generic one branches every 8 columns and ran at ~1/3 IPC.
+template <int kEpi, bool kBuilder, int kBN, int kFast = 0>
 __global__ void __launch_bounds__(Cfg<kEpi, kBuilder>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -228,10 +240,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tt) {
             if (lane == 0) EWVIT_TRACE(0, tt, 0);
-            const int m_t = w % p.tiles_m;            // m fastest: a CTA keeps its column tile (and its staged
-            const int wn = w / p.tiles_m;             // bias) for many consecutive tiles
-            const int n_t = wn % p.tiles_n;
-            const int sp = wn / p.tiles_n;
+            int m_t, n_t, sp;
+            if (!decode_tile(p, w, m_t, n_t, sp)) continue;
             const int kb0 = sp * p.kb_per_split;
             const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             int tx = 0, ty = 0, img = 0;
@@ -320,12 +330,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.b_res) ewvit::mbar_wait(ewvit::smem_u32(bres_bar), 0);
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tt) {
             if (lane == 0) EWVIT_TRACE(1, tt, 0);
-            const int wn = w / p.tiles_m;
-            const int sp = wn / p.tiles_n;
+            int m_t, n_t, sp;
+            if (!decode_tile(p, w, m_t, n_t, sp)) continue;
+            (void)m_t;
             const int kb0 = sp * p.kb_per_split;
             const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             // columns past N are zero-filled B rows: shrink the MMA's N to the valid part (multiple of 16)
-            const int n_valid = min(kBN, p.N - (wn % p.tiles_n) * kBN);
+            const int n_valid = min(kBN, p.N - n_t * kBN);
             const uint32_t idesc = ewvit::umma_idesc_bf16(BM, (uint32_t)((n_valid + 15) & ~15));
             ewvit::mbar_wait(ewvit::smem_u32(&tempty[acc]), acc_phase ^ 1);
             ewvit::tc_fence_after();
@@ -580,10 +591,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
             if ((it & 1) != acc) continue;
             if (q == 2 && lane == 0) EWVIT_TRACE(2 + grp, it, 0);
-            const int m_t = w % p.tiles_m;
-            const int wn = w / p.tiles_m;
-            const int n_t = wn % p.tiles_n;
-            const int sp = wn / p.tiles_n;
+            int m_t, n_t, sp;
+            if (!decode_tile(p, w, m_t, n_t, sp)) continue;
 
             if ((kEpi == EPI_CONV || kEpi == EPI_BB) && n_t != cur_nt) {   // (re)stage the per-channel scale/shift of this column tile
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -647,6 +656,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 ewvit::tmem_ld_wait();
                 const int col0 = n_t * kBN + c * 32;
+                if (kEpi == EPI_BB && kFast != 0) {
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 sh = *reinterpret_cast<const float4 *>(&g_shift[c * 32 + 4 * i]);
+                        f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + sh.x;
+                        f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + sh.y;
+                        f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + sh.z;
+                        f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + sh.w;
+                    }
+                    if (kFast == 1) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float th;
+                            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(f[i]));
+                            f[i] = fmaf(f[i], th, f[i]);
+                        }
+                    } else if (p.residual_bf16) {
+#pragma unroll
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            const __nv_bfloat162 *rp = reinterpret_cast<const __nv_bfloat162 *>(&rcur[g8]);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 r2 = __bfloat1622float2(rp[i]);
+                                f[g8 * 8 + 2 * i] += r2.x;
+                                f[g8 * 8 + 2 * i + 1] += r2.y;
+                            }
+                        }
+                    }
+                    if (zero) {              // padded-flat output: the one-pixel border stays zero
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = 0.f;
+                    }
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const __nv_bfloat162 bb = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                        pk[i] = *reinterpret_cast<const uint32_t *>(&bb);
+                    }
+                    stage_chunk_bf16(stg, lane, pk);
+                    if (lane == 0) {
+                        if (p.a_mode == A_FLAT || p.a_mode == A_SCALED) tma_store_2d(&tmC, stg, p.col_off + col0, m_t * BM + q * 32);
+                        else tma_store_4d(&tmC, stg, p.col_off + col0, st_x, st_y, st_img);
+                    }
+                    continue;
+                }
                 if (kEpi == EPI_BB) {
                     // bias (+ SiLU / ReLU) (+ bf16 residual) -> bf16; columns past N are computed but never stored
                     uint32_t pk[16];
@@ -656,7 +711,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float f8[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) f8[i] = __uint_as_float(v[g8 * 8 + i]) + g_shift[c * 32 + g8 * 8 + i];
-                        if (p.act == 3 && !(p.dbg & 2)) {
+                        if (p.act == 4) {        // SiLU on pre-halved operands: f8 = v/2, silu(v) = h*tanh(h) + h  (2 ops per value)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float th;
+                                asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(f8[i]));
+                                f8[i] = fmaf(f8[i], th, f8[i]);
+                            }
+                        } else if (p.act == 3 && !(p.dbg & 2)) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) f8[i] = ewvit::silu_fast(f8[i]);
                         } else if (p.act == 1) {
@@ -823,13 +885,13 @@ static inline int b_box_rows(int N, int bn, int tiles_n) {
 static long long *g_trace = nullptr;
 static int g_dbg = 0;
 
-template <int kEpi, bool kBuilder, int kBN>
+template <int kEpi, bool kBuilder, int kBN, int kFast = 0>
 int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, GemmParams p, cudaStream_t stream) {
     static bool attr_set[64] = {false};
     int dev = 0;
     EWVIT_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        EWVIT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kBuilder, kBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kEpi, kBuilder>::kSmemBytes));
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kBuilder, kBN, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kEpi, kBuilder>::kSmemBytes));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     if (p.b_tile_bytes <= 0) p.b_tile_bytes = kBN * BK * 2;
@@ -855,7 +917,7 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
     long long grid = ewvit_num_sms();
     if (grid > work) grid = work;
     if (grid <= 0) return EWVIT_OK;
-    gemm_tc_kernel<kEpi, kBuilder, kBN><<<(unsigned)grid, Cfg<kEpi, kBuilder>::kThreads, Cfg<kEpi, kBuilder>::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+    gemm_tc_kernel<kEpi, kBuilder, kBN, kFast><<<(unsigned)grid, Cfg<kEpi, kBuilder>::kThreads, Cfg<kEpi, kBuilder>::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }
@@ -864,9 +926,15 @@ int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMa
                 int bn = BN) {
     if (epi == EPI_CONV) return launch_gemm_t<EPI_CONV, false, 128>(tmA, tmB, tmC, p, stream);
     if (epi == EPI_BB) {
-        if (p.a_mode == A_IM2COL || p.a_mode == A_SCALED)
-            return bn == 256 ? launch_gemm_t<EPI_BB, true, 256>(tmA, tmB, tmC, p, stream) : launch_gemm_t<EPI_BB, true, 128>(tmA, tmB, tmC, p, stream);
-        return bn == 256 ? launch_gemm_t<EPI_BB, false, 256>(tmA, tmB, tmC, p, stream) : launch_gemm_t<EPI_BB, false, 128>(tmA, tmB, tmC, p, stream);
+        const int fast = (g_dbg & 256) ? 0 : (p.act == 4 && !p.residual_bf16) ? 1 : p.act == 0 ? 2 : 0;
+        const bool builder = p.a_mode == A_IM2COL || p.a_mode == A_SCALED;
+#define EWVIT_BB(B_, N_)                                                                              \
+        (fast == 1 ? launch_gemm_t<EPI_BB, B_, N_, 1>(tmA, tmB, tmC, p, stream)                           \
+         : fast == 2 ? launch_gemm_t<EPI_BB, B_, N_, 2>(tmA, tmB, tmC, p, stream)                         \
+                     : launch_gemm_t<EPI_BB, B_, N_, 0>(tmA, tmB, tmC, p, stream))
+        if (builder) return bn == 256 ? EWVIT_BB(true, 256) : EWVIT_BB(true, 128);
+        return bn == 256 ? EWVIT_BB(false, 256) : EWVIT_BB(false, 128);
+#undef EWVIT_BB
     }
     if (epi == EPI_PARTIAL) return launch_gemm_t<EPI_PARTIAL, false, 128>(tmA, tmB, tmC, p, stream);
     return launch_gemm_t<EPI_LINEAR, false, 128>(tmA, tmB, tmC, p, stream);
@@ -1111,7 +1179,7 @@ static int conv_nhwc_impl(const void *x, const void *w, int n, int h, int wd, in
                   "ewvit_conv_nhwc_bf16: supports 1x1/stride 1 and 3x3/stride 1|2 (got k=%d s=%d)", ksize, stride);
     EWVIT_REQUIRE(cin % 8 == 0 && cout % 8 == 0, EWVIT_ERR_UNSUPPORTED,
                   "ewvit_conv_nhwc_bf16: channel counts must be multiples of 8 (got cin=%d cout=%d)", cin, cout);
-    EWVIT_REQUIRE(act == 0 || act == 1 || act == 3, EWVIT_ERR_INVALID_ARG, "ewvit_conv_nhwc_bf16: act must be 0 (none), 1 (relu) or 3 (silu)");
+    EWVIT_REQUIRE(act == 0 || act == 1 || act == 3 || act == 4, EWVIT_ERR_INVALID_ARG, "ewvit_conv_nhwc_bf16: act must be 0 (none), 1 (relu), 3 (silu) or 4 (silu, halved operands)");
     EWVIT_REQUIRE(ewvit_aligned16(x) && ewvit_aligned16(w) && ewvit_aligned16(y) && ewvit_aligned16(residual), EWVIT_ERR_INVALID_ARG,
                   "ewvit_conv_nhwc_bf16: pointers must be 16-byte aligned");
     int rc = ewvit_check_device();

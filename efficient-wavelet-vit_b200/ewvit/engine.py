@@ -308,6 +308,18 @@ class NativeEffNetV2:
         w, b = _fold_conv_bn(head[0], head[1])
         self.ops.append(("conv1", w.flatten(1).to(torch.bfloat16).to(dev).contiguous(), b.to(dev), "silu", False, False))
         self.layout = self._plan_layouts(os.environ.get("EWVIT_WINDOW_CONV", "1") == "1")
+        # SiLU epilogues evaluate h*tanh(h) + h with h = v/2: fold the 1/2 into weights and bias (exact: a power of two)
+        for i, op in enumerate(self.ops):
+            if op[0] == "conv3" and op[4] == "silu" and not self._is_c24(i):
+                self.ops[i] = ("conv3", op[1] * 0.5, op[2] * 0.5, op[3], "silu_h", op[5], op[6])
+                if i in self.win_w:
+                    self.win_w[i] = self.win_w[i] * 0.5
+            elif op[0] == "conv1" and op[3] == "silu":
+                self.ops[i] = ("conv1", op[1] * 0.5, op[2] * 0.5, "silu_h", op[4], op[5])
+
+    def _is_c24(self, i):
+        op = self.ops[i]
+        return self.c24 and op[0] == "conv3" and self.cin3[i] == 24 and op[1].shape[0] == 24 and op[3] == 1 and op[4] == "silu"
 
     def _plan_layouts(self, enable):
         """Per op (in_padded, out_padded).  The stride-1 3x3 convs with cin < 64 (stages 1-2 of V2-S) run fastest on
@@ -385,8 +397,7 @@ class NativeEffNetV2:
                             out = self._zero_bordered(i, (n, (hp - 1) // stride + 3, (wp - 1) // stride + 3, w.shape[0]))
                         x = ops.conv_nhwc_bf16_ex(x, self.win_w[i] if window else w, 3, stride, self.cin3[i], bias=b, act=act,
                                                   residual=block_in if res else None, out=out, in_padded=in_p, out_padded=out_p)
-                    elif self.cin3[i] == 24 and w.shape[0] == 24 and stride == 1 and act == "silu" and self.c24 \
-                            and (not res or block_in is x):
+                    elif self._is_c24(i) and (not res or block_in is x):
                         x = ops.conv3x3_c24(x, w, b, residual=res)       # direct conv on warp-level MMAs (N = 24)
                     else:
                         x = ops.conv_nhwc_bf16(x, w, 3, stride, bias=b, act=act, residual=block_in if res else None)

@@ -303,7 +303,7 @@ def video_head(fused, space, freq, videos, k, classifier=None):
     return mf, ms, mq, logits
 
 
-ACT_BB = {None: 0, "none": 0, "relu": 1, "silu": 3}
+ACT_BB = {None: 0, "none": 0, "relu": 1, "silu": 3, "silu_h": 4}      # silu_h: SiLU, weights and bias pre-halved by the caller
 
 
 def conv_nhwc_bf16(x, w, ksize, stride, bias=None, act=None, residual=None, out=None):

@@ -228,7 +228,9 @@ EWVIT_API int ewvit_video_head_fwd(const float *fused, const float *space, const
  * ksize 1 (stride 1): w [cout, cin] bf16.   ksize 3 (pad 1, stride 1|2; cin <= 64 or cin % 64 == 0):
  * w [cout, Kpad] bf16 with the dense tap-major index k = (ky*3+kx)*cin + c, zero-padded to Kpad = ceil(9*cin/64)*64.
  *   x [n, h, wd, cin] bf16    y, residual [n, ho, wo, cout] bf16 (residual may be NULL)    bias [cout] fp32 or NULL
- *   act: 0 none, 1 ReLU, 3 SiLU.    cin, cout multiples of 8 (tails are zero-filled by TMA and masked). */
+ *   act: 0 none, 1 ReLU, 3 SiLU, 4 SiLU on pre-halved operands (the caller passes w/2 and bias/2 -- exact in bf16/fp32 --
+ *        and the epilogue evaluates silu(v) = h*tanh(h) + h with h = v/2 directly: one multiply less per output).
+ *   cin, cout multiples of 8 (tails are zero-filled by TMA and masked). */
 EWVIT_API int ewvit_conv_nhwc_bf16(const void *x, const void *w, int n, int h, int wd, int cin, int cout, int ksize,
                                    int stride, const float *bias, int act, const void *residual, void *y, void *stream);
 
