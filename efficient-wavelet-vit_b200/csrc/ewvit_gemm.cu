@@ -638,6 +638,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ewvit::tc_fence_after();
             if (q == 2 && lane == 0) EWVIT_TRACE(2 + grp, it, 1);
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kBN);
+            if (kEpi == EPI_CONV) {
+                // MWT convs: the chunk loop is unrolled and software-pipelined -- the TMEM load of chunk c+1 is in flight while
+                // chunk c goes through BN + ReLU, packing, staging and its TMA store (320-thread kernel: registers to spare)
+                constexpr int kChunks = kColsPerGroup / 32;
+                const float lo = p.act ? 0.f : -INFINITY;
+                const float keep = zero ? 0.f : 1.f;
+                uint32_t v2[2][32];
+                ewvit::tmem_ld_32x32(t_row + half * kColsPerGroup, v2[0]);
+#pragma unroll
+                for (int ci = 0; ci < kChunks; ++ci) {
+                    const int c = half * kChunks + ci;
+                    ewvit::tmem_ld_wait();
+                    if (ci + 1 < kChunks) ewvit::tmem_ld_32x32(t_row + (c + 1) * 32, v2[(ci + 1) & 1]);
+                    if (n_t * kBN + c * 32 >= p.N) continue;          // warp-uniform: nothing valid in this chunk
+                    const uint32_t (&v)[32] = v2[ci & 1];
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 sc = *reinterpret_cast<const float4 *>(&g_scale[c * 32 + 4 * i]);
+                        const float4 sh = *reinterpret_cast<const float4 *>(&g_shift[c * 32 + 4 * i]);
+                        const float f0 = fmaxf(fmaf(__uint_as_float(v[4 * i + 0]), sc.x, sh.x), lo) * keep;
+                        const float f1 = fmaxf(fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y), lo) * keep;
+                        const float f2 = fmaxf(fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z), lo) * keep;
+                        const float f3 = fmaxf(fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w), lo) * keep;
+                        const __nv_bfloat162 b0 = __floats2bfloat162_rn(f0, f1), b1 = __floats2bfloat162_rn(f2, f3);
+                        pk[2 * i] = *reinterpret_cast<const uint32_t *>(&b0);
+                        pk[2 * i + 1] = *reinterpret_cast<const uint32_t *>(&b1);
+                    }
+                    stage_chunk_bf16(stg, lane, pk);
+                    if (lane == 0) {
+                        const int col0 = n_t * kBN + c * 32;
+                        if (p.a_mode == A_FLAT || p.a_mode == A_SCALED) tma_store_2d(&tmC, stg, p.col_off + col0, m_t * BM + q * 32);
+                        else tma_store_4d(&tmC, stg, p.col_off + col0, st_x, st_y, st_img);
+                    }
+                }
+            } else
 #pragma unroll 1
             for (int c = half * (kColsPerGroup / 32); c < (half + 1) * (kColsPerGroup / 32); ++c) {
                 if ((kEpi == EPI_BB || kEpi == EPI_CONV) && n_t * kBN + c * 32 >= p.N) continue;   // warp-uniform: nothing valid in this chunk
