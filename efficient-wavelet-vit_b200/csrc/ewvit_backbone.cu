@@ -398,7 +398,8 @@ constexpr int kSeThreads = 512;
 constexpr int kSeMaxC = 12 * 128;          // FC1 keeps one weight row (c / 128 float4 per lane) in registers
 __global__ void __launch_bounds__(kSeThreads) se_gate_kernel(const float *__restrict__ pooled, const float *__restrict__ w1,
                                                              const float *__restrict__ b1, const float *__restrict__ w2t,
-                                                             const float *__restrict__ b2, float *__restrict__ gate, int n, int c, int sq) {
+                                                             const float *__restrict__ b2, float *__restrict__ gate, int n, int c, int sq,
+                                                             int out_bf16) {
     extern __shared__ __align__(16) float se_sm[];
     float *s_pool = se_sm;                 // [kSeF][c]
     float *s_hid = se_sm + kSeF * c;       // [kSeF][sq]
@@ -476,7 +477,15 @@ __global__ void __launch_bounds__(kSeThreads) se_gate_kernel(const float *__rest
                 o.y = 1.f / (1.f + __expf(-acc[f].y));
                 o.z = 1.f / (1.f + __expf(-acc[f].z));
                 o.w = 1.f / (1.f + __expf(-acc[f].w));
-                reinterpret_cast<float4 *>(gate + (long long)(f0 + f) * c)[i] = o;
+                if (out_bf16) {
+                    const __nv_bfloat162 q0 = __floats2bfloat162_rn(o.x, o.y), q1 = __floats2bfloat162_rn(o.z, o.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t *>(&q0);
+                    pk.y = *reinterpret_cast<const uint32_t *>(&q1);
+                    reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(gate) + (long long)(f0 + f) * c)[i] = pk;
+                } else {
+                    reinterpret_cast<float4 *>(gate + (long long)(f0 + f) * c)[i] = o;
+                }
             }
     }
 }
@@ -632,7 +641,7 @@ extern "C" int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const floa
         EWVIT_CUDA_OK(cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         if (dev >= 0 && dev < 64) se_attr[dev] = true;
     }
-    se_gate_kernel<<<(unsigned)((n + kSeF - 1) / kSeF), kSeThreads, gate_smem, (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, gate_ws, n, c, sq);
+    se_gate_kernel<<<(unsigned)((n + kSeF - 1) / kSeF), kSeThreads, gate_smem, (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, gate_ws, n, c, sq, 0);
     EWVIT_LAUNCH_OK();
     const long long total8 = (long long)n * hw * (c / 8);
     long long blocks = (total8 + 255) / 256;
@@ -645,7 +654,7 @@ extern "C" int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const floa
 
 // Squeeze-excitation gate only (the scaling is fused into ewvit_conv1x1_gated_nhwc_bf16).
 extern "C" int ewvit_se_gate_fwd(const float *pooled, const float *w1, const float *b1, const float *w2t, const float *b2, int n,
-                                 int c, int sq, float *gate, void *stream) {
+                                 int c, int sq, void *gate, int gate_bf16, void *stream) {
     EWVIT_REQUIRE(n >= 0 && c > 0 && sq > 0, EWVIT_ERR_INVALID_ARG, "ewvit_se_gate_fwd: bad sizes");
     if (n == 0) return EWVIT_OK;
     EWVIT_REQUIRE(pooled && w1 && b1 && w2t && b2 && gate && ewvit_aligned16(gate) && ewvit_aligned16(pooled) &&
@@ -662,7 +671,7 @@ extern "C" int ewvit_se_gate_fwd(const float *pooled, const float *w1, const flo
         EWVIT_CUDA_OK(cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         if (dev >= 0 && dev < 64) se_attr[dev] = true;
     }
-    se_gate_kernel<<<(unsigned)((n + kSeF - 1) / kSeF), kSeThreads, gate_smem, (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, gate, n, c, sq);
+    se_gate_kernel<<<(unsigned)((n + kSeF - 1) / kSeF), kSeThreads, gate_smem, (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, static_cast<float *>(gate), n, c, sq, gate_bf16 ? 1 : 0);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }

@@ -94,7 +94,8 @@ struct GemmParams {
     // multiply it in place by the per-(frame, channel) gate before the MMA consumes it, so the separate x *= gate
     // pass (one read + one write of the expanded tensor) disappears; tile geometry = A_FLAT
     const __nv_bfloat16 *a_ptr;
-    const float *a_gate;   // [frames, K] fp32
+    const void *a_gate;    // [frames, K] fp32, or bf16 when a_gate_bf16
+    int a_gate_bf16;
     int a_hw;              // rows (pixels) per frame
     int a_k;               // K = row pitch of A and of the gate
     int flat3;           // A_FLAT 3x3 conv, "row-shared" taps: one ring slot = (dy, channel chunk) holds ONE window of
@@ -430,8 +431,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if ((stage & (kBuilderSlots - 1)) != pair) continue;
                     const uint32_t phase = (g / (uint32_t)nstages) & 1u;
                     const bool kin = kb * BK + j * 8 < p.a_k;               // K tail: the tile holds zeros there
-                    const float *gk = p.a_gate + kb * BK;
                     const uint32_t a_base = smem_base + stage * kStageB + chunk_off;
+                    if (p.a_gate_bf16) {
+                        // bf16 gates: one 16-byte load and four packed multiplies per 8-channel chunk (the product of two bf16
+                        // values is exact in fp32, so HMUL2.BF16 rounds exactly like the fp32 path)
+                        const __nv_bfloat16 *gk = static_cast<const __nv_bfloat16 *>(p.a_gate) + kb * BK;
+                        bool waited = false;
+#pragma unroll
+                        for (int b4 = 0; b4 < 2; ++b4) {
+                            uint4 gq[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                gq[i] = make_uint4(0u, 0u, 0u, 0u);
+                                if (kin) gq[i] = __ldg(reinterpret_cast<const uint4 *>(gk + goff[b4 * 8 + i]));
+                            }
+                            if (!waited) {
+                                ewvit::mbar_wait(ewvit::smem_u32(&hfull[stage]), phase);
+                                waited = true;
+                            }
+                            uint4 v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
+                                             : "r"(a_base + (b4 * 8 + i) * 1024) : "memory");
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const __nv_bfloat162 *vp = reinterpret_cast<const __nv_bfloat162 *>(&v[i]);
+                                const __nv_bfloat162 *gp2 = reinterpret_cast<const __nv_bfloat162 *>(&gq[i]);
+                                const __nv_bfloat162 o0 = __hmul2(vp[0], gp2[0]), o1 = __hmul2(vp[1], gp2[1]);
+                                const __nv_bfloat162 o2 = __hmul2(vp[2], gp2[2]), o3 = __hmul2(vp[3], gp2[3]);
+                                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + (b4 * 8 + i) * 1024),
+                                             "r"(*reinterpret_cast<const uint32_t *>(&o0)), "r"(*reinterpret_cast<const uint32_t *>(&o1)),
+                                             "r"(*reinterpret_cast<const uint32_t *>(&o2)), "r"(*reinterpret_cast<const uint32_t *>(&o3))
+                                             : "memory");
+                            }
+                        }
+                    } else {
+                    const float *gk = static_cast<const float *>(p.a_gate) + kb * BK;
                     bool waited = false;
 #pragma unroll
                     for (int b4 = 0; b4 < 4; ++b4) {
@@ -467,6 +503,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                          "r"(*reinterpret_cast<const uint32_t *>(&o2)), "r"(*reinterpret_cast<const uint32_t *>(&o3))
                                          : "memory");
                         }
+                    }
                     }
                     ewvit::fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
                     __syncwarp();
@@ -1448,14 +1485,14 @@ extern "C" int ewvit_debug_set_trace(void *device_buffer) {
 
 // 1x1 convolution behind a squeeze-excitation block: y = act(((x * gate[frame]) W^T) + bias) + residual, with the gate
 // applied while the A operand tile is assembled (no separate scaling pass over the expanded tensor).
-extern "C" int ewvit_conv1x1_gated_nhwc_bf16(const void *x, const float *gate, const void *w, int n, int hw, int cin, int cout,
-                                             const float *bias, int act, const void *residual, void *y, void *stream) {
+extern "C" int ewvit_conv1x1_gated_nhwc_bf16(const void *x, const void *gate, int gate_bf16, const void *w, int n, int hw, int cin,
+                                             int cout, const float *bias, int act, const void *residual, void *y, void *stream) {
     EWVIT_REQUIRE(n >= 0 && hw > 0 && cin > 0 && cout > 0, EWVIT_ERR_INVALID_ARG, "ewvit_conv1x1_gated_nhwc_bf16: bad sizes");
     if (n == 0) return EWVIT_OK;
     EWVIT_REQUIRE(x && gate && w && y, EWVIT_ERR_INVALID_ARG, "ewvit_conv1x1_gated_nhwc_bf16: NULL pointer");
     EWVIT_REQUIRE(cin % 8 == 0 && cout % 8 == 0, EWVIT_ERR_UNSUPPORTED,
                   "ewvit_conv1x1_gated_nhwc_bf16: channel counts must be multiples of 8 (got cin=%d cout=%d)", cin, cout);
-    EWVIT_REQUIRE(act == 0 || act == 1 || act == 3, EWVIT_ERR_INVALID_ARG, "ewvit_conv1x1_gated_nhwc_bf16: act must be 0, 1 or 3");
+    EWVIT_REQUIRE(act == 0 || act == 1 || act == 3 || act == 4, EWVIT_ERR_INVALID_ARG, "ewvit_conv1x1_gated_nhwc_bf16: act must be 0, 1, 3 or 4");
     EWVIT_REQUIRE(ewvit_aligned16(x) && ewvit_aligned16(gate) && ewvit_aligned16(w) && ewvit_aligned16(y) && ewvit_aligned16(residual),
                   EWVIT_ERR_INVALID_ARG, "ewvit_conv1x1_gated_nhwc_bf16: pointers must be 16-byte aligned");
     int rc = ewvit_check_device();
@@ -1467,6 +1504,7 @@ extern "C" int ewvit_conv1x1_gated_nhwc_bf16(const void *x, const float *gate, c
     p.a_mode = A_SCALED;
     p.a_ptr = static_cast<const __nv_bfloat16 *>(x);
     p.a_gate = gate;
+    p.a_gate_bf16 = gate_bf16 ? 1 : 0;
     p.a_hw = hw;
     p.a_k = cin;
     p.N = cout;

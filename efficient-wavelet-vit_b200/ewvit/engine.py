@@ -419,7 +419,7 @@ class NativeEffNetV2:
                     x = ops.dwconv3x3(x, w, b, stride, pooled=pooled)
                 elif kind == "se":
                     if self.fuse_se:
-                        gate = ops.se_gate(pooled, op[1], op[2], op[3], op[4])
+                        gate = ops.se_gate(pooled, op[1], op[2], op[3], op[4], bf16=True)
                     else:
                         ops.se_apply(x, pooled, op[1], op[2], op[3], op[4])
                 elif kind == "conv1g":

@@ -430,16 +430,16 @@ def se_apply(x, pooled, w1, b1, w2t, b2, gate_ws=None):
     return x
 
 
-def se_gate(pooled, w1, b1, w2t, b2, out=None):
-    """gate [n,c] fp32 = sigmoid(W2 silu(W1 pooled + b1) + b2)."""
+def se_gate(pooled, w1, b1, w2t, b2, out=None, bf16=False):
+    """gate [n,c] = sigmoid(W2 silu(W1 pooled + b1) + b2), fp32 or (bf16=True) bf16."""
     for t, nm in ((pooled, "pooled"), (w1, "w1"), (b1, "b1"), (w2t, "w2t"), (b2, "b2")):
         _check_f32(t, nm)
     n, c = pooled.shape
     if out is None:
-        out = torch.empty((n, c), dtype=torch.float32, device=pooled.device)
+        out = torch.empty((n, c), dtype=torch.bfloat16 if bf16 else torch.float32, device=pooled.device)
     with torch.cuda.device(pooled.device):
         check(load().ewvit_se_gate_fwd(pooled.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2t.data_ptr(), b2.data_ptr(), n, c,
-                                       w1.shape[0], out.data_ptr(), _stream()), "ewvit_se_gate_fwd")
+                                       w1.shape[0], out.data_ptr(), int(out.dtype == torch.bfloat16), _stream()), "ewvit_se_gate_fwd")
     return out
 
 
@@ -447,7 +447,10 @@ def conv1x1_gated(x, gate, w, bias=None, act=None, residual=None, out=None):
     """y = act(((x * gate[frame]) @ w^T) + bias) + residual; x [n,h,w,cin] bf16, gate [n,cin] fp32, w [cout,cin] bf16."""
     _check_bf16(x, "x", 4)
     _check_bf16(w, "w", 2)
-    _check_f32(gate, "gate")
+    if gate.dtype == torch.bfloat16:
+        _check_bf16(gate, "gate", 2)
+    else:
+        _check_f32(gate, "gate")
     n, h, wd, cin = x.shape
     cout = w.shape[0]
     if gate.shape != (n, cin) or w.shape[1] != cin:
@@ -460,7 +463,7 @@ def conv1x1_gated(x, gate, w, bias=None, act=None, residual=None, out=None):
             raise EwvitError("conv1x1_gated: residual must match the output")
     bias = _f32_or_none(bias, "bias", cout)
     with torch.cuda.device(x.device):
-        check(load().ewvit_conv1x1_gated_nhwc_bf16(x.data_ptr(), gate.data_ptr(), w.data_ptr(), n, h * wd, cin, cout, _ptr(bias),
+        check(load().ewvit_conv1x1_gated_nhwc_bf16(x.data_ptr(), gate.data_ptr(), int(gate.dtype == torch.bfloat16), w.data_ptr(), n, h * wd, cin, cout, _ptr(bias),
                                                    ACT_BB[act], _ptr(residual), out.data_ptr(), _stream()),
               "ewvit_conv1x1_gated_nhwc_bf16")
     return out

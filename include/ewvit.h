@@ -271,16 +271,17 @@ EWVIT_API int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const float
                                        const float *b2, int n, int hw, int c, int sq, float *gate_ws, void *stream);
 
 /* Squeeze-excitation gate only: gate[n, c] = sigmoid(W2 silu(W1 pooled[n] + b1) + b2) (same operands as
- * ewvit_se_apply_nhwc_bf16); the scaling itself is then fused into ewvit_conv1x1_gated_nhwc_bf16. */
+ * ewvit_se_apply_nhwc_bf16); the scaling itself is then fused into ewvit_conv1x1_gated_nhwc_bf16.
+ * gate_bf16 != 0: the gates are written as bf16 (what the gated conv multiplies fastest), else fp32. */
 EWVIT_API int ewvit_se_gate_fwd(const float *pooled, const float *w1, const float *b1, const float *w2t, const float *b2, int n,
-                                int c, int sq, float *gate, void *stream);
+                                int c, int sq, void *gate, int gate_bf16, void *stream);
 
 /* 1x1 convolution behind a squeeze-excitation block (MBConv project conv):
  *   y = act(((x * gate[frame]) W^T) + bias) + residual
- * x [n, hw, cin] bf16, gate [n, cin] fp32, w [cout, cin] bf16, y/residual [n, hw, cout] bf16.  The gate is applied while
+ * x [n, hw, cin] bf16, gate [n, cin] fp32 (gate_bf16 == 0) or bf16 (gate_bf16 != 0), w [cout, cin] bf16, y/residual [n, hw, cout] bf16.  The gate is applied while
  * the A operand tile is assembled in shared memory, so the expanded tensor is read exactly once. */
-EWVIT_API int ewvit_conv1x1_gated_nhwc_bf16(const void *x, const float *gate, const void *w, int n, int hw, int cin, int cout,
-                                            const float *bias, int act, const void *residual, void *y, void *stream);
+EWVIT_API int ewvit_conv1x1_gated_nhwc_bf16(const void *x, const void *gate, int gate_bf16, const void *w, int n, int hw, int cin,
+                                            int cout, const float *bias, int act, const void *residual, void *y, void *stream);
 
 /* Debug aid for kernel bring-up: when non-NULL, CTA 0 of every subsequent tensor-core GEMM/conv launch writes
  * clock64 stamps of its warp roles to this device buffer ([6 roles][64 tiles][4] int64).  NULL switches it off. */

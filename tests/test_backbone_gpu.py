@@ -203,6 +203,15 @@ def test_gated_project_conv(ops, c, cout, hw, res):
     got = ops.conv1x1_gated(_nhwc(x).cuda(), gate.cuda().contiguous(), wt.flatten(1).contiguous().cuda(), bias=b.cuda(),
                             residual=_nhwc(r).cuda() if res else None)
     _close(got.permute(0, 3, 1, 2), ref)
+    # bf16 gates (what the engine uses): same contract with the gate rounded to bf16 first
+    gb = gate.bfloat16()
+    xs = (x.float() * gb.float().view(n, c, 1, 1)).bfloat16().float()
+    ref = F.conv2d(xs, wt.float(), b)
+    if res:
+        ref = ref + r.float()
+    got = ops.conv1x1_gated(_nhwc(x).cuda(), gb.cuda().contiguous(), wt.flatten(1).contiguous().cuda(), bias=b.cuda(),
+                            residual=_nhwc(r).cuda() if res else None)
+    _close(got.permute(0, 3, 1, 2), ref)
 
 
 def test_se_gate(ops):
@@ -213,6 +222,9 @@ def test_se_gate(ops):
     ref = torch.sigmoid(F.silu(pooled @ w1.t() + b1) @ w2.t() + b2)
     got = ops.se_gate(pooled.cuda(), w1.cuda(), b1.cuda(), w2.t().contiguous().cuda(), b2.cuda())
     _close(got, ref, tol=1e-3, bf16_out=False)
+    got = ops.se_gate(pooled.cuda(), w1.cuda(), b1.cuda(), w2.t().contiguous().cuda(), b2.cuda(), bf16=True)
+    assert got.dtype == torch.bfloat16
+    _close(got, ref, tol=1e-3, bf16_out=True)
 
 
 def test_native_backbone_matches_torchvision(dama_sd, golden):
