@@ -29,10 +29,19 @@ __device__ __forceinline__ void matvec_t(const float *__restrict__ wt, int ldw, 
                                          float (&acc)[kFpc]) {
 #pragma unroll
     for (int f = 0; f < kFpc; ++f) acc[f] = 0.f;
-    for (int k = 0; k < in_dim; ++k) {
-        const float w = __ldg(wt + (long long)k * ldw + j);
+    // the weight column is requested 16 rows at a time (independent L2 loads in flight; one at a time left this kernel
+    // waiting on ~4000 dependent L2 round trips per CTA)
+    for (int k0 = 0; k0 < in_dim; k0 += 16) {
+        float w[16];
 #pragma unroll
-        for (int f = 0; f < kFpc; ++f) acc[f] = fmaf(w, x[f * ldx + k], acc[f]);
+        for (int u = 0; u < 16; ++u) w[u] = k0 + u < in_dim ? __ldg(wt + (long long)(k0 + u) * ldw + j) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            if (k0 + u < in_dim) {
+#pragma unroll
+                for (int f = 0; f < kFpc; ++f) acc[f] = fmaf(w[u], x[f * ldx + k0 + u], acc[f]);
+            }
+        }
     }
 }
 

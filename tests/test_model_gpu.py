@@ -203,6 +203,26 @@ def test_detector_many_videos_one_pass(detector, dama_sd):
         check(f"8x6 videos [{k}]", out[k], ref[k])
 
 
+def test_full_size_config3_matches_oracle_and_is_deterministic(detector, dama_sd):
+    """BASELINE configs[2] at full size: 8 videos x 64 frames, batch_size 8 (reference: 8 serial chunks of 64 frames; here one
+    native pass of 512 frames).  Logits / fused features against the fp32 CPU oracle within the bf16 tolerance, identical
+    real/fake decisions wherever the reference logit is farther from 0 than the tolerance, and bit-identical results
+    across two runs (no atomics, fixed reduction orders)."""
+    x = seeded_randn((8, 64, 3, 224, 224), 97)
+    xc = x.cuda()
+    with torch.no_grad():
+        a = detector(xc, 8, "dynamic")
+        b = detector(xc, 8, "dynamic")
+    for k in ("logits", "fused", "space", "freq"):
+        assert torch.equal(a[k], b[k]), f"{k}: two runs differ"
+    ref = O.detector_forward(dama_sd, x, 8, "dynamic")
+    for k in ("fused", "space", "freq", "logits"):
+        check(f"512 frames [{k}]", a[k], ref[k])
+    tol = TOL * float(ref["logits"].abs().max())
+    decided = ref["logits"].abs() > tol
+    assert torch.equal((a["logits"].cpu() >= 0)[decided], (ref["logits"] >= 0)[decided])
+
+
 def test_chunk_limit_raises_like_reference(detector):
     """Quirk (ii): B * batch_size > 64 frames per chunk raises RuntimeError (sfe.py:158-159)."""
     with pytest.raises(RuntimeError, match="must match the size"):
