@@ -13,49 +13,84 @@ __device__ __forceinline__ float silu(float x) { return ewvit::silu_fast(x); }
 // ---- stem: Conv2d(3 -> cout<=32, 3x3, stride 2, pad 1) + bias + SiLU, fp32 NCHW frames -> bf16 NHWC
 //      (also the fp32 -> bf16 conversion of the input; torchvision features[0], sfe.py:150)
 constexpr int kStemMaxC = 32;
-__global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict__ x, const float *__restrict__ w,
+constexpr int kStemPx = 4;      // output pixels per thread (consecutive columns): every weight read from shared memory feeds 4 FMAs
+__global__ void __launch_bounds__(128) stem_conv_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                         const float *__restrict__ bias, __nv_bfloat16 *__restrict__ y,
                                                         int n, int h, int wd, int ho, int wo, int cout, int pad) {
-    __shared__ float s_w[kStemMaxC * 27];
-    __shared__ float s_b[kStemMaxC];
-    for (int i = threadIdx.x; i < cout * 27; i += blockDim.x) s_w[i] = w[i];
-    if (threadIdx.x < cout) s_b[threadIdx.x] = bias[threadIdx.x];
+    // weights transposed to [27][cout] so that 4 consecutive output channels are one 16-byte shared-memory read;
+    // pre-halved for the h*tanh(h)+h form of SiLU
+    __shared__ __align__(16) float s_w[27 * kStemMaxC];
+    __shared__ __align__(16) float s_b[kStemMaxC];
+    for (int i = threadIdx.x; i < cout * 27; i += blockDim.x) s_w[(i % 27) * kStemMaxC + i / 27] = 0.5f * w[i];
+    if (threadIdx.x < cout) s_b[threadIdx.x] = 0.5f * bias[threadIdx.x];
     __syncthreads();
-    const long long total = (long long)n * ho * wo;
+    const int wq = (wo + kStemPx - 1) / kStemPx;                 // pixel quads per output row
+    const long long total = (long long)n * ho * wq;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int ox = (int)(idx % wo);
-        const long long t = idx / wo;
+        const int qx = (int)(idx % wq);
+        const long long t = idx / wq;
         const int oy = (int)(t % ho);
         const long long img = t / ho;
-        float in[27];
+        const int ox0 = qx * kStemPx;
+        // input patch: 3 channels x 3 rows x 9 columns (columns 2*ox0 - 1 .. 2*ox0 + 7)
+        float in[3][3][2 * kStemPx + 1];
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
+            for (int dy = 0; dy < 3; ++dy) {
+                const int iy = 2 * oy + dy - 1;
+                const float *row = x + ((img * 3 + c) * h + (iy >= 0 && iy < h ? iy : 0)) * (long long)wd;
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const int iy = 2 * oy + dy - 1, ix = 2 * ox + dx - 1;
-                    in[c * 9 + dy * 3 + dx] = (iy >= 0 && iy < h && ix >= 0 && ix < wd) ? __ldg(x + ((img * 3 + c) * h + iy) * wd + ix) : 0.f;
+                for (int j = 0; j < 2 * kStemPx + 1; ++j) {
+                    const int ix = 2 * ox0 + j - 1;
+                    in[c][dy][j] = (iy >= 0 && iy < h && ix >= 0 && ix < wd) ? __ldg(row + ix) : 0.f;
                 }
-        // pad = 1: padded-flat output [n, ho+2, wo+2, cout] (interior written, the zero border belongs to the caller)
-        __nv_bfloat16 *py = y + ((img * (ho + 2 * pad) + oy + pad) * (wo + 2 * pad) + ox + pad) * cout;
-        for (int c0 = 0; c0 < cout; c0 += 8) {
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float a = s_b[c0 + j];
-#pragma unroll
-                for (int k = 0; k < 27; ++k) a = fmaf(s_w[(c0 + j) * 27 + k], in[k], a);
-                o[j] = silu(a);
             }
-            uint4 pk;
-            __nv_bfloat162 b0 = __floats2bfloat162_rn(o[0], o[1]), b1 = __floats2bfloat162_rn(o[2], o[3]);
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(o[4], o[5]), b3 = __floats2bfloat162_rn(o[6], o[7]);
-            pk.x = *reinterpret_cast<uint32_t *>(&b0);
-            pk.y = *reinterpret_cast<uint32_t *>(&b1);
-            pk.z = *reinterpret_cast<uint32_t *>(&b2);
-            pk.w = *reinterpret_cast<uint32_t *>(&b3);
-            *reinterpret_cast<uint4 *>(py + c0) = pk;
+        // pad = 1: padded-flat output [n, ho+2, wo+2, cout] (interior written, the zero border belongs to the caller)
+        __nv_bfloat16 *py = y + ((img * (ho + 2 * pad) + oy + pad) * (wo + 2 * pad) + ox0 + pad) * cout;
+        for (int c0 = 0; c0 < cout; c0 += 8) {
+            float acc[kStemPx][8];
+#pragma unroll
+            for (int p4 = 0; p4 < kStemPx; ++p4)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[p4][j] = s_b[c0 + j];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int k = c * 9 + dy * 3 + dx;
+                        const float4 w0 = *reinterpret_cast<const float4 *>(&s_w[k * kStemMaxC + c0]);
+                        const float4 w1 = *reinterpret_cast<const float4 *>(&s_w[k * kStemMaxC + c0 + 4]);
+#pragma unroll
+                        for (int p4 = 0; p4 < kStemPx; ++p4) {
+                            const float v = in[c][dy][2 * p4 + dx];
+                            acc[p4][0] = fmaf(w0.x, v, acc[p4][0]); acc[p4][1] = fmaf(w0.y, v, acc[p4][1]);
+                            acc[p4][2] = fmaf(w0.z, v, acc[p4][2]); acc[p4][3] = fmaf(w0.w, v, acc[p4][3]);
+                            acc[p4][4] = fmaf(w1.x, v, acc[p4][4]); acc[p4][5] = fmaf(w1.y, v, acc[p4][5]);
+                            acc[p4][6] = fmaf(w1.z, v, acc[p4][6]); acc[p4][7] = fmaf(w1.w, v, acc[p4][7]);
+                        }
+                    }
+#pragma unroll
+            for (int p4 = 0; p4 < kStemPx; ++p4) {
+                if (ox0 + p4 >= wo) break;
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float th;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(acc[p4][j]));
+                    o[j] = fmaf(acc[p4][j], th, acc[p4][j]);
+                }
+                uint4 pk;
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(o[0], o[1]), b1 = __floats2bfloat162_rn(o[2], o[3]);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(o[4], o[5]), b3 = __floats2bfloat162_rn(o[6], o[7]);
+                pk.x = *reinterpret_cast<uint32_t *>(&b0);
+                pk.y = *reinterpret_cast<uint32_t *>(&b1);
+                pk.z = *reinterpret_cast<uint32_t *>(&b2);
+                pk.w = *reinterpret_cast<uint32_t *>(&b3);
+                *reinterpret_cast<uint4 *>(py + p4 * cout + c0) = pk;
+            }
         }
     }
 }
@@ -520,11 +555,11 @@ static int stem_impl(const float *x, int n, int h, int wd, const float *w, const
     int rc = ewvit_check_device();
     if (rc != EWVIT_OK) return rc;
     const int ho = (h - 1) / 2 + 1, wo = (wd - 1) / 2 + 1;
-    const long long total = (long long)n * ho * wo;
-    long long blocks = (total + 255) / 256;
+    const long long total = (long long)n * ho * ((wo + kStemPx - 1) / kStemPx);
+    long long blocks = (total + 127) / 128;
     const long long cap = (long long)ewvit_num_sms() * 32;
     if (blocks > cap) blocks = cap;
-    stem_conv_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, w, bias, static_cast<__nv_bfloat16 *>(y), n, h, wd, ho, wo, cout, out_padded ? 1 : 0);
+    stem_conv_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(x, w, bias, static_cast<__nv_bfloat16 *>(y), n, h, wd, ho, wo, cout, out_padded ? 1 : 0);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }
