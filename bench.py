@@ -282,6 +282,39 @@ def main():
             step_e2e()
         e2e_ms = timed(step_e2e, args.steps)
 
+        # ---- row f-3: the same end-to-end steps from raw uint8 frames (ToTensor + Normalize fused into the DWT and stem kernels):
+        #      a quarter of the bytes cross PCIe; same overlap scheme as above
+        u8_host = torch.randint(0, 256, (VIDEOS, FRAMES, 3, SIDE, SIDE), generator=gen, dtype=torch.uint8).pin_memory()
+        u8_stage = [torch.empty((VIDEOS, FRAMES, 3, SIDE, SIDE), dtype=torch.uint8, device=dev) for _ in range(2)]
+        u8_state = {"i": 0, "primed": False}
+
+        def issue_copy_u8(slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                u8_stage[slot].copy_(u8_host, non_blocking=True)
+                copied[slot].record(copy_stream)
+
+        def step_e2e_u8():
+            i = u8_state["i"]
+            slot = i & 1
+            if not u8_state["primed"]:
+                issue_copy_u8(slot)
+                u8_state["primed"] = True
+            issue_copy_u8(slot ^ 1)
+            torch.cuda.current_stream().wait_event(copied[slot])
+            out = model.forward_uint8(u8_stage[slot], BATCH_SIZE)
+            consumed[slot].record()
+            if world > 1:
+                dist.all_gather(gathered, out["logits"])
+            logits_host.copy_(out["logits"], non_blocking=True)
+            u8_state["i"] = i + 1
+            return logits_host
+
+        torch.cuda.synchronize()
+        for _ in range(2):
+            step_e2e_u8()
+        e2e_u8_ms = timed(step_e2e_u8, args.steps)
+
         # ---- standalone fused DWT, BASELINE configs[1]: 256x3x224x224 fp32, all six outputs materialised
         dwt = None
         if rank == 0:
@@ -357,6 +390,9 @@ def main():
         "data": "synthetic", "config": workload_config(world), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": VIDEOS * 4,
                 "ms_per_step": e2e_ms / args.steps},
+        "e2e_uint8_input": {"value": world * n_frames * args.steps / (e2e_u8_ms / 1e3), "unit": "frames/s",
+                            "h2d_bytes_per_step": u8_host.numel(), "d2h_bytes_per_step": VIDEOS * 4, "ms_per_step": e2e_u8_ms / args.steps,
+                            "note": "extension (SURVEY 8f-3): model.forward_uint8, ToTensor+Normalize fused into the DWT and stem kernels"},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, **extra,
     }
     print(json.dumps(line))

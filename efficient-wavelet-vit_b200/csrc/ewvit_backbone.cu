@@ -14,13 +14,22 @@ __device__ __forceinline__ float silu(float x) { return ewvit::silu_fast(x); }
 //      (also the fp32 -> bf16 conversion of the input; torchvision features[0], sfe.py:150)
 constexpr int kStemMaxC = 32;
 constexpr int kStemPx = 4;      // output pixels per thread (consecutive columns): every weight read from shared memory feeds 4 FMAs
-__global__ void __launch_bounds__(128) stem_conv_kernel(const float *__restrict__ x, const float *__restrict__ w,
+// TIn = float: normalised fp32 frames.  TIn = unsigned char: raw frames, ((u / 255) - mean[c]) / std[c] applied on load
+// (config/transforms.py:97-98), zero padding applied AFTER the normalisation as in the reference.
+template <typename TIn>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const TIn *__restrict__ x, const float *__restrict__ w,
                                                         const float *__restrict__ bias, __nv_bfloat16 *__restrict__ y,
-                                                        int n, int h, int wd, int ho, int wo, int cout, int pad) {
+                                                        int n, int h, int wd, int ho, int wo, int cout, int pad,
+                                                        const float *__restrict__ mean, const float *__restrict__ stdv) {
     // weights transposed to [27][cout] so that 4 consecutive output channels are one 16-byte shared-memory read;
     // pre-halved for the h*tanh(h)+h form of SiLU
     __shared__ __align__(16) float s_w[27 * kStemMaxC];
     __shared__ __align__(16) float s_b[kStemMaxC];
+    __shared__ float s_lut[sizeof(TIn) == 1 ? 3 * 256 : 1];      // uint8 frames: per-channel value table, the reference's arithmetic
+    if (sizeof(TIn) == 1) {
+        for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x)
+            s_lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.f), __ldg(mean + (i >> 8))), __ldg(stdv + (i >> 8)));
+    }
     for (int i = threadIdx.x; i < cout * 27; i += blockDim.x) s_w[(i % 27) * kStemMaxC + i / 27] = 0.5f * w[i];
     if (threadIdx.x < cout) s_b[threadIdx.x] = 0.5f * bias[threadIdx.x];
     __syncthreads();
@@ -39,11 +48,16 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float *__restrict_
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
                 const int iy = 2 * oy + dy - 1;
-                const float *row = x + ((img * 3 + c) * h + (iy >= 0 && iy < h ? iy : 0)) * (long long)wd;
+                const TIn *row = x + ((img * 3 + c) * h + (iy >= 0 && iy < h ? iy : 0)) * (long long)wd;
 #pragma unroll
                 for (int j = 0; j < 2 * kStemPx + 1; ++j) {
                     const int ix = 2 * ox0 + j - 1;
-                    in[c][dy][j] = (iy >= 0 && iy < h && ix >= 0 && ix < wd) ? __ldg(row + ix) : 0.f;
+                    float v = 0.f;
+                    if (iy >= 0 && iy < h && ix >= 0 && ix < wd) {
+                        if (sizeof(TIn) == 1) v = s_lut[c * 256 + (int)__ldg(row + ix)];
+                        else v = (float)__ldg(row + ix);
+                    }
+                    in[c][dy][j] = v;
                 }
             }
         // pad = 1: padded-flat output [n, ho+2, wo+2, cout] (interior written, the zero border belongs to the caller)
@@ -546,8 +560,8 @@ __global__ void __launch_bounds__(256) se_scale_kernel(__nv_bfloat16 *__restrict
 
 }  // namespace
 
-static int stem_impl(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout, void *y, int out_padded,
-                     void *stream) {
+static int stem_impl(const void *x, bool u8, const float *mean, const float *stdv, int n, int h, int wd, const float *w, const float *bias,
+                     int cout, void *y, int out_padded, void *stream) {
     EWVIT_REQUIRE(n >= 0 && h > 0 && wd > 0, EWVIT_ERR_INVALID_ARG, "ewvit_stem_conv_fwd: bad sizes");
     if (n == 0) return EWVIT_OK;
     EWVIT_REQUIRE(x && w && bias && y && ewvit_aligned16(y), EWVIT_ERR_INVALID_ARG, "ewvit_stem_conv_fwd: NULL or misaligned pointer");
@@ -559,19 +573,32 @@ static int stem_impl(const float *x, int n, int h, int wd, const float *w, const
     long long blocks = (total + 127) / 128;
     const long long cap = (long long)ewvit_num_sms() * 32;
     if (blocks > cap) blocks = cap;
-    stem_conv_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(x, w, bias, static_cast<__nv_bfloat16 *>(y), n, h, wd, ho, wo, cout, out_padded ? 1 : 0);
+    if (u8)
+        stem_conv_kernel<unsigned char><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char *>(x), w, bias,
+                                                                                           static_cast<__nv_bfloat16 *>(y), n, h, wd, ho, wo, cout,
+                                                                                           out_padded ? 1 : 0, mean, stdv);
+    else
+        stem_conv_kernel<float><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(static_cast<const float *>(x), w, bias,
+                                                                                   static_cast<__nv_bfloat16 *>(y), n, h, wd, ho, wo, cout,
+                                                                                   out_padded ? 1 : 0, nullptr, nullptr);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }
 
 extern "C" int ewvit_stem_conv_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
                                    void *y, void *stream) {
-    return stem_impl(x, n, h, wd, w, bias, cout, y, 0, stream);
+    return stem_impl(x, false, nullptr, nullptr, n, h, wd, w, bias, cout, y, 0, stream);
 }
 
 extern "C" int ewvit_stem_conv_padded_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
                                           void *y, void *stream) {
-    return stem_impl(x, n, h, wd, w, bias, cout, y, 1, stream);
+    return stem_impl(x, false, nullptr, nullptr, n, h, wd, w, bias, cout, y, 1, stream);
+}
+
+extern "C" int ewvit_stem_conv_u8_fwd(const uint8_t *x, const float *mean, const float *stdv, int n, int h, int wd, const float *w,
+                                      const float *bias, int cout, void *y, int out_padded, void *stream) {
+    EWVIT_REQUIRE(mean && stdv, EWVIT_ERR_INVALID_ARG, "ewvit_stem_conv_u8_fwd: mean/std missing");
+    return stem_impl(x, true, mean, stdv, n, h, wd, w, bias, cout, y, out_padded, stream);
 }
 
 template <int SC, int STRIDE>

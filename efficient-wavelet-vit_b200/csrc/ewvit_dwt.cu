@@ -21,6 +21,7 @@ constexpr float kS = 0.70710677f;   // fp32(1/sqrt(2)) -- the reference's filter
 constexpr int kStages = 3;
 constexpr int kMaxBandsPerTile = 8;
 constexpr int kThreads = 256;
+constexpr int kMaxU8Channels = 4;
 
 struct Haar4 {
     float ll, lh, hl, hh;
@@ -40,7 +41,9 @@ __device__ __forceinline__ Haar4 haar2x2(float a, float b, float c, float d) {
 }
 
 struct Dwt3Params {
-    const float *x;
+    const void *x;           // fp32 planes, or uint8 planes when the kernel is instantiated with kU8
+    const float *mean, *stdv;   // kU8: per-channel normalisation, value = ((u / 255) - mean[c]) / std[c], c = plane % channels
+    int channels;
     float *ll1, *hf1, *ll2, *hf2, *ll3, *hf3;
     long long total_bands;   // planes * h/8
     int bands_per_plane;     // h/8
@@ -49,12 +52,25 @@ struct Dwt3Params {
     int bands_per_tile;
 };
 
+// kU8: the frames arrive as uint8 (what a decoder produces) and the ToTensor + Normalize arithmetic of the reference's input
+// pipeline (config/transforms.py:97-98: x/255, then (x - mean) / std, each rounded separately) happens on load -- a quarter
+// of the input bytes cross PCIe and HBM.
+template <bool kU8>
 __global__ void __launch_bounds__(kThreads, 1) dwt3_haar_kernel(const Dwt3Params p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long full_bar[kStages];
 
+    // kU8: 256-entry lookup table per channel, built with exactly the reference's arithmetic (two IEEE divisions and a
+    // subtraction per entry) so that the per-sample conversion is one shared-memory read and still bit-identical
+    __shared__ float s_lut[kU8 ? kMaxU8Channels * 256 : 1];
     const int tid = threadIdx.x;
-    const uint32_t band_bytes = 32u * (uint32_t)p.w;
+    if (kU8) {
+        for (int i = tid; i < p.channels * 256; i += kThreads) {
+            const int ch = i >> 8, u = i & 255;
+            s_lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.f), __ldg(p.mean + ch)), __ldg(p.stdv + ch));
+        }
+    }
+    const uint32_t band_bytes = (kU8 ? 8u : 32u) * (uint32_t)p.w;
     const uint32_t stage_bytes = band_bytes * (uint32_t)p.bands_per_tile;
     const uint32_t smem_base = ewvit::smem_u32(smem_raw);
 
@@ -116,6 +132,16 @@ __global__ void __launch_bounds__(kThreads, 1) dwt3_haar_kernel(const Dwt3Params
 
             // ---- 8x8 block from shared memory
             float v[8][8];
+            if (kU8) {
+                const unsigned char *blk8 = smem_raw + (size_t)stage * stage_bytes + ((size_t)bl * 8 * w + j * 8);
+                const float *lut = s_lut + ((int)(plane % p.channels) << 8);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint2 q = *reinterpret_cast<const uint2 *>(blk8 + r * w);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[r][k] = lut[((k < 4 ? q.x : q.y) >> (8 * (k & 3))) & 0xffu];
+                }
+            } else {
             const float *blk = tile_s + (size_t)bl * 8 * w + j * 8;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
@@ -124,6 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwt3_haar_kernel(const Dwt3Params
                 const float4 lo = swap ? q1 : q0, hi = swap ? q0 : q1;
                 v[r][0] = lo.x; v[r][1] = lo.y; v[r][2] = lo.z; v[r][3] = lo.w;
                 v[r][4] = hi.x; v[r][5] = hi.y; v[r][6] = hi.z; v[r][7] = hi.w;
+            }
             }
 
             // ---- level 1: 4x4 coefficients per subband
@@ -236,8 +263,8 @@ extern "C" int ewvit_dwt_haar_fwd(const float *x, int64_t planes, int h, int w, 
     return EWVIT_OK;
 }
 
-extern "C" int ewvit_dwt3_haar_fwd(const float *x, int64_t planes, int h, int w, float *ll1, float *hf1,
-                                   float *ll2, float *hf2, float *ll3, float *hf3, void *stream) {
+static int dwt3_impl(const void *x, bool u8, const float *mean, const float *stdv, int channels, int64_t planes, int h, int w, float *ll1,
+                     float *hf1, float *ll2, float *hf2, float *ll3, float *hf3, void *stream) {
     EWVIT_REQUIRE(planes >= 0 && h >= 0 && w >= 0, EWVIT_ERR_INVALID_ARG,
                   "ewvit_dwt3_haar_fwd: negative size (planes=%lld h=%d w=%d)", (long long)planes, h, w);
     EWVIT_REQUIRE(h % 8 == 0 && w % 8 == 0, EWVIT_ERR_UNSUPPORTED,
@@ -254,11 +281,12 @@ extern "C" int ewvit_dwt3_haar_fwd(const float *x, int64_t planes, int h, int w,
 
     Dwt3Params p;
     p.x = x; p.ll1 = ll1; p.hf1 = hf1; p.ll2 = ll2; p.hf2 = hf2; p.ll3 = ll3; p.hf3 = hf3;
+    p.mean = mean; p.stdv = stdv; p.channels = channels > 0 ? channels : 1;
     p.bands_per_plane = h / 8;
     p.total_bands = (long long)planes * p.bands_per_plane;
     p.w = w;
     p.bw = w / 8;
-    const int band_bytes = 32 * w;
+    const int band_bytes = (u8 ? 8 : 32) * w;
     int bpt = (64 * 1024) / band_bytes;           // <= 64 KiB per stage
     if (bpt > kMaxBandsPerTile) bpt = kMaxBandsPerTile;
     if (bpt < 1) bpt = 1;
@@ -269,12 +297,27 @@ extern "C" int ewvit_dwt3_haar_fwd(const float *x, int64_t planes, int h, int w,
     int dev = 0;
     EWVIT_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        EWVIT_CUDA_OK(cudaFuncSetAttribute(dwt3_haar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(dwt3_haar_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(dwt3_haar_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     long long grid = ewvit_num_sms();
     if (grid > p.total_bands) grid = p.total_bands;
-    dwt3_haar_kernel<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    if (u8) dwt3_haar_kernel<true><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    else dwt3_haar_kernel<false><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(p);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
+}
+
+extern "C" int ewvit_dwt3_haar_fwd(const float *x, int64_t planes, int h, int w, float *ll1, float *hf1,
+                                   float *ll2, float *hf2, float *ll3, float *hf3, void *stream) {
+    return dwt3_impl(x, false, nullptr, nullptr, 1, planes, h, w, ll1, hf1, ll2, hf2, ll3, hf3, stream);
+}
+
+extern "C" int ewvit_dwt3_haar_u8_fwd(const uint8_t *x, const float *mean, const float *stdv, int channels, int64_t planes, int h, int w,
+                                      float *ll1, float *hf1, float *ll2, float *hf2, float *ll3, float *hf3, void *stream) {
+    EWVIT_REQUIRE(mean && stdv && channels > 0 && channels <= kMaxU8Channels, EWVIT_ERR_INVALID_ARG,
+                  "ewvit_dwt3_haar_u8_fwd: needs mean/std and 1..4 channels");
+    EWVIT_REQUIRE((8 * w) % 16 == 0, EWVIT_ERR_UNSUPPORTED, "ewvit_dwt3_haar_u8_fwd: w must be even");
+    return dwt3_impl(x, true, mean, stdv, channels, planes, h, w, ll1, hf1, ll2, hf2, ll3, hf3, stream);
 }

@@ -40,6 +40,8 @@ SIGNATURES = {
     "ewvit_dama_tail_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, P, c_float, P, P, P, P]),
     "ewvit_conv_nhwc_bf16": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, P]),
     "ewvit_conv3x3_c24_fwd": (c_int, [P, P, c_int, P, c_int, c_int, c_int, c_int, P, P]),
+    "ewvit_dwt3_haar_u8_fwd": (c_int, [P, P, P, c_int, c_int64, c_int, c_int, P, P, P, P, P, P, P]),
+    "ewvit_stem_conv_u8_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P, c_int, P, c_int, P]),
     "ewvit_stem_conv_fwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P]),
     "ewvit_stem_conv_padded_fwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P]),
     "ewvit_conv_nhwc_bf16_ex": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, c_int, c_int, P]),

@@ -154,8 +154,8 @@ class MwtRunner:
             self._ws[key] = ws
         return ws
 
-    def forward(self, frames, out=None):
-        """frames [n,3,H,W] fp32 CUDA (H, W multiples of 8) -> [n, dim] fp32."""
+    def forward(self, frames, out=None, norm=None):
+        """frames [n,3,H,W] fp32 CUDA (or uint8 with norm=(mean, std)), H, W multiples of 8 -> [n, dim] fp32."""
         n, c, h, w = frames.shape
         if c != 3 or h % 8 or w % 8:
             raise EwvitError(f"native MWT needs [n,3,H,W] with H,W multiples of 8 (got {tuple(frames.shape)})")
@@ -163,7 +163,7 @@ class MwtRunner:
         h1, w1, d = h // 2, w // 2, self.dim
         hf = ws["hf"]
         with stage("mwt.dwt3"):
-            ops.dwt3_haar(frames, out={"hf1": hf[0], "hf2": hf[1], "hf3": hf[2]}, want=("hf1", "hf2", "hf3"))
+            ops.dwt3_haar(frames, out={"hf1": hf[0], "hf2": hf[1], "hf3": hf[2]}, want=("hf1", "hf2", "hf3"), norm=norm)
         for lvl in range(3):
             with stage("mwt.head"):
                 hfl = hf[lvl].view(n, 9, h >> (lvl + 1), w >> (lvl + 1))
@@ -369,8 +369,8 @@ class NativeEffNetV2:
             self._padbuf[key] = t
         return t
 
-    def forward(self, frames):
-        """fp32 [n,3,H,W] -> bf16 NHWC [n, H/32, W/32, C_out]."""
+    def forward(self, frames, norm=None):
+        """fp32 [n,3,H,W] (or uint8 with norm=(mean, std)) -> bf16 NHWC [n, H/32, W/32, C_out]."""
         block_in = None      # input of the current residual block
         x = None
         pooled = None
@@ -383,9 +383,9 @@ class NativeEffNetV2:
                     if out_p:
                         n, _, h, wd = frames.shape
                         buf = self._zero_bordered(i, (n, (h - 1) // 2 + 3, (wd - 1) // 2 + 3, op[1].shape[0]))
-                        x = ops.stem_conv(frames, op[1], op[2], out=buf, out_padded=True)
+                        x = ops.stem_conv(frames, op[1], op[2], out=buf, out_padded=True, norm=norm)
                     else:
-                        x = ops.stem_conv(frames, op[1], op[2])
+                        x = ops.stem_conv(frames, op[1], op[2], norm=norm)
                     block_in = x
                 elif kind == "conv3":
                     _, w, b, stride, act, res, ends = op
@@ -532,19 +532,21 @@ class SfeRunner:
         res = ops.linear_bf16(ws["tok"], self.fm_w, shift=self.fm_b, act="relu", out=out if self.fm_w.shape[0] == self.feat_dim else None)
         return res if res.shape[1] == self.feat_dim else res[:, : self.feat_dim].contiguous()
 
-    def features(self, frames):
-        """fp32 frames [n,3,H,W] -> bf16 [n, 62720] NHWC-flattened backbone features."""
+    def features(self, frames, norm=None):
+        """fp32 frames [n,3,H,W] (uint8 with norm on the native backbone) -> bf16 [n, 62720] NHWC-flattened backbone features."""
         if isinstance(self.backbone, NativeEffNetV2):
-            f = self.backbone.forward(frames)                    # NHWC bf16
+            f = self.backbone.forward(frames, norm=norm)         # NHWC bf16
             return f.reshape(f.shape[0], -1)
+        if frames.dtype == torch.uint8:
+            raise EwvitError("uint8 frames need the native EfficientNetV2-S backbone")
         x = frames.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
         f = self.backbone(x)                                     # [n, C, ph, pw], channels-last memory
         n = f.shape[0]
         return f.permute(0, 2, 3, 1).reshape(n, -1)              # view when channels-last
 
-    def forward(self, frames, pos_index, out=None):
+    def forward(self, frames, pos_index, out=None, norm=None):
         with stage("sfe.backbone"):
-            feat = self.features(frames)
+            feat = self.features(frames, norm=norm)
             if not feat.is_contiguous():
                 feat = feat.contiguous()
         return self.head(feat, pos_index, out)
@@ -612,7 +614,7 @@ class DamaRunner:
             self._pos_cache[key] = t
         return t
 
-    def process_frames(self, frames, pos_index):
+    def process_frames(self, frames, pos_index, norm=None):
         """frames [n,3,H,W] -> (fused, space, freq) each [n, dim] fp32 (``_process_frame``, dama.py:130-169)."""
         if self.overlap and TIMER is None:
             # the two branches are independent until the fusion tail: run the frequency branch on a side stream so
@@ -622,17 +624,17 @@ class DamaRunner:
             main = torch.cuda.current_stream()
             self.side_stream.wait_stream(main)
             with torch.cuda.stream(self.side_stream):
-                freq = self.mwt.forward(frames)
-            space = self.sfe.forward(frames, pos_index)
+                freq = self.mwt.forward(frames, norm=norm)
+            space = self.sfe.forward(frames, pos_index, norm=norm)
             main.wait_stream(self.side_stream)
         else:
-            space = self.sfe.forward(frames, pos_index)
-            freq = self.mwt.forward(frames)
+            space = self.sfe.forward(frames, pos_index, norm=norm)
+            freq = self.mwt.forward(frames, norm=norm)
         with stage("dama.tail"):
             return ops.dama_tail(space, freq, self.wpack, self.heads, self.depth, LN_EPS)
 
-    def forward_frames(self, x, batch_size):
-        """x [B,K,3,H,W] fp32 CUDA -> per-frame (fused, space, freq) [B*K, dim] in (b, k) order."""
+    def forward_frames(self, x, batch_size, norm=None):
+        """x [B,K,3,H,W] fp32 CUDA (or uint8 with norm=(mean, std)) -> per-frame (fused, space, freq) [B*K, dim] in (b, k) order."""
         b, k = x.shape[:2]
         check_chunk_limit(b, k, batch_size, self.sfe.emb_dim)
         frames = x.reshape(b * k, *x.shape[2:])
@@ -641,11 +643,11 @@ class DamaRunner:
         pos = self.pos_index(b, k, batch_size, x.device)
         n = b * k
         if n <= MACRO_BATCH:
-            return self.process_frames(frames, pos)
+            return self.process_frames(frames, pos, norm=norm)
         outs = [torch.empty((n, self.dim), dtype=torch.float32, device=x.device) for _ in range(3)]
         for s in range(0, n, MACRO_BATCH):
             e = min(s + MACRO_BATCH, n)
-            part = self.process_frames(frames[s:e], pos[s:e])
+            part = self.process_frames(frames[s:e], pos[s:e], norm=norm)
             for o, p in zip(outs, part):
                 o[s:e].copy_(p)
         return tuple(outs)
@@ -660,8 +662,8 @@ class DetectorRunner:
         self.classifier = (f("classifier.0.weight"), f("classifier.0.bias"), f("classifier.3.weight").reshape(-1).contiguous(),
                            f("classifier.3.bias"))
 
-    def forward(self, x, batch_size):
+    def forward(self, x, batch_size, norm=None):
         b, k = x.shape[:2]
-        fused, space, freq = self.dama.forward_frames(x, batch_size)
+        fused, space, freq = self.dama.forward_frames(x, batch_size, norm=norm)
         mf, ms, mq, logits = ops.video_head(fused, space, freq, b, k, self.classifier)
         return {"logits": logits, "fused": mf, "space": ms, "freq": mq}

@@ -39,14 +39,27 @@ def dwt_haar(x: torch.Tensor):
     return ll, yh
 
 
-def dwt3_haar(x: torch.Tensor, out=None, want=("ll1", "hf1", "ll2", "hf2", "ll3", "hf3")):
-    """Three chained Haar levels in one HBM pass.  x [N,C,H,W] fp32, H and W multiples of 8.
+def _check_norm(norm, c, name):
+    if norm is None or len(norm) != 2:
+        raise EwvitError(f"{name}: uint8 frames need norm=(mean, std), fp32 CUDA tensors of {c} values")
+    for t in norm:
+        _require_cuda(t, "norm")
+        if t.dtype != torch.float32 or t.numel() != c or not t.is_contiguous():
+            raise EwvitError(f"{name}: norm tensors must be contiguous fp32 with {c} values")
+
+
+def dwt3_haar(x: torch.Tensor, out=None, want=("ll1", "hf1", "ll2", "hf2", "ll3", "hf3"), norm=None):
+    """Three chained Haar levels in one HBM pass.  x [N,C,H,W] fp32 (or uint8 with norm=(mean, std): the ToTensor +
+    Normalize arithmetic happens on load), H and W multiples of 8.
 
     Returns a dict with the requested subbands (ll_k [N,C,H/2^k,W/2^k], hf_k [N,C,3,H/2^k,W/2^k]).
     ``out`` may carry preallocated tensors under the same keys."""
     _require_cuda(x, "x")
-    if x.dtype != torch.float32 or x.dim() != 4:
-        raise EwvitError("dwt3_haar: x must be fp32 [N,C,H,W]")
+    u8 = x.dtype == torch.uint8
+    if not (u8 or x.dtype == torch.float32) or x.dim() != 4:
+        raise EwvitError("dwt3_haar: x must be fp32 or uint8 [N,C,H,W]")
+    if u8:
+        _check_norm(norm, x.shape[1], "dwt3_haar")
     x = x.contiguous()
     n, c, h, w = x.shape
     res = {}
@@ -64,9 +77,14 @@ def dwt3_haar(x: torch.Tensor, out=None, want=("ll1", "hf1", "ll2", "hf2", "ll3"
             else:
                 res[key] = torch.empty(shape, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(load().ewvit_dwt3_haar_fwd(x.data_ptr(), n * c, h, w, _ptr(res["ll1"]), _ptr(res["hf1"]),
-                                         _ptr(res["ll2"]), _ptr(res["hf2"]), _ptr(res["ll3"]), _ptr(res["hf3"]),
-                                         _stream()), "ewvit_dwt3_haar_fwd")
+        if u8:
+            check(load().ewvit_dwt3_haar_u8_fwd(x.data_ptr(), norm[0].data_ptr(), norm[1].data_ptr(), c, n * c, h, w, _ptr(res["ll1"]),
+                                                _ptr(res["hf1"]), _ptr(res["ll2"]), _ptr(res["hf2"]), _ptr(res["ll3"]), _ptr(res["hf3"]),
+                                                _stream()), "ewvit_dwt3_haar_u8_fwd")
+        else:
+            check(load().ewvit_dwt3_haar_fwd(x.data_ptr(), n * c, h, w, _ptr(res["ll1"]), _ptr(res["hf1"]),
+                                             _ptr(res["ll2"]), _ptr(res["hf2"]), _ptr(res["ll3"]), _ptr(res["hf3"]),
+                                             _stream()), "ewvit_dwt3_haar_fwd")
     return {k: v for k, v in res.items() if v is not None}
 
 
@@ -375,9 +393,16 @@ def conv3x3_c24(x, w, bias, residual=False, out=None):
     return out
 
 
-def stem_conv(x, w, bias, out=None, out_padded=False):
-    """fp32 NCHW frames [n,3,h,w] -> bf16 NHWC [n,h/2,w/2,cout]: conv3x3 s2 + bias + SiLU."""
-    _check_f32(x, "x")
+def stem_conv(x, w, bias, out=None, out_padded=False, norm=None):
+    """fp32 NCHW frames [n,3,h,w] (or uint8 frames with norm=(mean, std)) -> bf16 NHWC [n,h/2,w/2,cout]: conv3x3 s2 + bias + SiLU."""
+    u8 = x.dtype == torch.uint8
+    if u8:
+        _require_cuda(x, "x")
+        if not x.is_contiguous() or x.dim() != 4:
+            raise EwvitError("stem_conv: x must be a contiguous [n,3,h,w] tensor")
+        _check_norm(norm, 3, "stem_conv")
+    else:
+        _check_f32(x, "x")
     _check_f32(w, "w")
     n, c, h, wd = x.shape
     cout = w.shape[0]
@@ -385,18 +410,18 @@ def stem_conv(x, w, bias, out=None, out_padded=False):
         raise EwvitError("stem_conv: expects 3 input channels and [cout,3,3,3] weights")
     bias = _f32_or_none(bias, "bias", cout)
     ho, wo = (h - 1) // 2 + 1, (wd - 1) // 2 + 1
-    if out_padded:
-        if out is None:
-            out = torch.zeros((n, ho + 2, wo + 2, cout), dtype=torch.bfloat16, device=x.device)
-        elif tuple(out.shape) != (n, ho + 2, wo + 2, cout) or out.dtype != torch.bfloat16 or not out.is_contiguous():
-            raise EwvitError("stem_conv: bad padded out tensor")
-        fn = load().ewvit_stem_conv_padded_fwd
-    else:
-        if out is None:
-            out = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
-        fn = load().ewvit_stem_conv_fwd
+    oshape = (n, ho + 2, wo + 2, cout) if out_padded else (n, ho, wo, cout)
+    if out is None:
+        out = (torch.zeros if out_padded else torch.empty)(oshape, dtype=torch.bfloat16, device=x.device)
+    elif tuple(out.shape) != oshape or out.dtype != torch.bfloat16 or not out.is_contiguous():
+        raise EwvitError("stem_conv: bad out tensor")
     with torch.cuda.device(x.device):
-        check(fn(x.data_ptr(), n, h, wd, w.data_ptr(), bias.data_ptr(), cout, out.data_ptr(), _stream()), "ewvit_stem_conv_fwd")
+        if u8:
+            check(load().ewvit_stem_conv_u8_fwd(x.data_ptr(), norm[0].data_ptr(), norm[1].data_ptr(), n, h, wd, w.data_ptr(), bias.data_ptr(),
+                                                cout, out.data_ptr(), int(out_padded), _stream()), "ewvit_stem_conv_u8_fwd")
+        else:
+            fn = load().ewvit_stem_conv_padded_fwd if out_padded else load().ewvit_stem_conv_fwd
+            check(fn(x.data_ptr(), n, h, wd, w.data_ptr(), bias.data_ptr(), cout, out.data_ptr(), _stream()), "ewvit_stem_conv_fwd")
     return out
 
 

@@ -81,6 +81,28 @@ class DeepfakeDetector(NativeMixin, nn.Module):
             fused = sfe_mean * gate[:, 0:1] + mwt_mean * gate[:, 1:2]
             return {"logits": self.classifier(fused), "sfe": sfe_mean, "mwt": mwt_mean, "model": "sfe_mwt"}
 
+    def forward_uint8(self, x, batch_size=None, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+        """Extension, not part of the reference API: score raw uint8 frames x [B,K,3,H,W].
+        The reference's input pipeline turns decoded frames into floats with ``ToTensor`` and ``Normalize(mean, std)``
+        (config/transforms.py:97-98) on the host; here that arithmetic happens on load inside the first two kernels (fused
+        DWT, backbone stem), so a quarter of the bytes cross PCIe and HBM.  Bit-identical to
+        ``forward(((x.float() / 255) - mean) / std, batch_size, 'dynamic')``.  Eval mode, CUDA, dynamic ablation only."""
+        from ewvit import EwvitError
+        if x.dtype != torch.uint8 or x.dim() != 5 or x.shape[2] != 3:
+            raise EwvitError("forward_uint8: x must be a uint8 tensor [B, K, 3, H, W]")
+        if batch_size is not None:
+            self.batch_size = batch_size
+        if self.training or not x.is_cuda:
+            raise EwvitError("forward_uint8 serves eval-mode CUDA calls only (there is no CPU path)")
+        key = (str(x.device), tuple(float(v) for v in mean), tuple(float(v) for v in std))
+        cache = self.__dict__.setdefault("_ewvit_norm", {})
+        norm = cache.get(key)
+        if norm is None:        # built once: a host -> device copy per call would serialise the caller's copy/compute overlap
+            norm = (torch.tensor(key[1], dtype=torch.float32, device=x.device), torch.tensor(key[2], dtype=torch.float32, device=x.device))
+            cache[key] = norm
+        self.ablation = "dynamic"
+        return self._native_runner(self._build_runner).forward(x.contiguous(), self.batch_size, norm=norm)
+
     def configure_ablation(self, ablation):
         if ablation in self.ablation_config:
             self.ablation = ablation

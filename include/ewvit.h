@@ -82,6 +82,13 @@ EWVIT_API int ewvit_dwt3_haar_fwd(const float *x, int64_t planes, int h, int w,
                         float *ll1, float *hf1, float *ll2, float *hf2, float *ll3, float *hf3,
                         void *stream);
 
+/* The same three levels straight from uint8 frames (row f-3: the step upstream of the path, reference
+ * config/transforms.py:97-98 `ToTensor` + `Normalize`): every sample is converted on load as
+ *   v = ((float(u) / 255) - mean[c]) / std[c],   c = plane % channels,  each operation rounded to fp32 separately
+ * which is bit-identical to torchvision's to_tensor().sub_(mean).div_(std).  mean, std: [channels] fp32 on the device. */
+EWVIT_API int ewvit_dwt3_haar_u8_fwd(const uint8_t *x, const float *mean, const float *stdv, int channels, int64_t planes, int h,
+                                     int w, float *ll1, float *hf1, float *ll2, float *hf2, float *ll3, float *hf3, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * bf16 tensor-core linear layer  (rows a-5, a-7: nn.Linear call sites network/sfe.py:155 patch_to_embedding,
  * sfe.py:52,54 to_qkv/to_out, sfe.py:31-37 FeedForward, sfe.py:141 feat_map; all `x @ W^T + b`)
@@ -258,6 +265,10 @@ EWVIT_API int ewvit_stem_conv_fwd(const float *x, int n, int h, int wd, const fl
 /* Same, writing the interior of a padded-flat output y [n, ho+2, wo+2, cout] (the caller zeroes the border once). */
 EWVIT_API int ewvit_stem_conv_padded_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
                                          void *y, void *stream);
+/* Stem from uint8 frames x [n,3,h,wd] with the same on-load normalisation as ewvit_dwt3_haar_u8_fwd (the conv's zero
+ * padding is applied after the normalisation, as in the reference); out_padded selects the padded-flat output layout. */
+EWVIT_API int ewvit_stem_conv_u8_fwd(const uint8_t *x, const float *mean, const float *stdv, int n, int h, int wd, const float *w,
+                                     const float *bias, int cout, void *y, int out_padded, void *stream);
 
 /* Depthwise 3x3 (pad 1, stride 1|2) + bias + SiLU, plus the squeeze of the SE block: pooled[n, c] = spatial mean of
  * the stored result (NULL to skip).  x [n,h,wd,c] bf16, w [9, c] fp32 (tap-major), y [n,ho,wo,c] bf16; c % 64 == 0. */

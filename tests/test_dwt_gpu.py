@@ -92,3 +92,18 @@ def test_config2_full_size_properties(ops):
     c = ops.dwt3_haar(torch.full((4, 3, 224, 224), 0.25, device="cuda"))
     assert torch.allclose(c["ll3"], torch.full_like(c["ll3"], 2.0), rtol=1e-6)
     assert all(float(c[f"hf{l}"].abs().max()) == 0.0 for l in (1, 2, 3))
+
+
+def test_fused_three_levels_from_uint8_frames_bitwise(ops):
+    """uint8 input + on-load ToTensor/Normalize (row f-3) == the fp32 kernel on torchvision-normalised frames, bit for bit"""
+    g = torch.Generator().manual_seed(7)
+    u = torch.randint(0, 256, (5, 3, 64, 48), generator=g, dtype=torch.uint8)
+    mean = torch.tensor([0.485, 0.456, 0.406])
+    std = torch.tensor([0.229, 0.224, 0.225])
+    xf = u.float().div(255).sub(mean.view(1, 3, 1, 1)).div(std.view(1, 3, 1, 1))        # to_tensor + normalize
+    ref = ops.dwt3_haar(xf.cuda())
+    got = ops.dwt3_haar(u.cuda(), norm=(mean.cuda(), std.cuda()))
+    for k in ref:
+        assert torch.equal(got[k], ref[k]), k
+    ll, hf = haar_dwt2(xf)
+    assert torch.equal(got["ll1"].cpu(), ll) and torch.equal(got["hf1"].cpu(), hf)

@@ -251,3 +251,20 @@ def test_ablation_modes_run_native_heads(detector):
     assert a["model"] == "sfe_only" and a["logits"].shape == (2, 1) and torch.isfinite(a["logits"]).all()
     assert b["model"] == "sfe_mwt" and b["logits"].shape == (2, 1) and b["sfe"].shape == (2, 128) and b["mwt"].shape == (2, 128)
     assert torch.isfinite(b["logits"]).all()
+
+
+def test_forward_uint8_equals_forward_on_normalised_frames(detector):
+    """forward_uint8 (normalisation fused into the DWT and stem kernels) is bit-identical to forward on host-normalised frames"""
+    g = torch.Generator().manual_seed(11)
+    u = torch.randint(0, 256, (2, 5, 3, 224, 224), generator=g, dtype=torch.uint8)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 1, 3, 1, 1)
+    xf = u.float().div(255).sub(mean).div(std)
+    with torch.no_grad():
+        ref = detector(xf.cuda(), 2, "dynamic")
+        got = detector.forward_uint8(u.cuda(), 2)
+    for k in ("logits", "fused", "space", "freq"):
+        assert torch.equal(got[k], ref[k]), k
+    from ewvit import EwvitError
+    with pytest.raises(EwvitError):
+        detector.forward_uint8(xf.cuda(), 2)
