@@ -637,7 +637,7 @@ extern "C" int ewvit_dwconv3x3_nhwc_bf16(const void *x, const float *w, const fl
     EWVIT_REQUIRE(2 * plane <= 190 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_dwconv3x3_nhwc_bf16: %dx%d input plane too large for the staged kernel", h, wd);
     // frames per pass: enough (frame, column, channel group) items for the 256 threads, within ~48 KB per stage
     int fb = 1;
-    while (fb < 8 && fb * wo * (sc / 4) < 224 && 2 * fb * plane <= 48 * 1024 && fb * 2 <= n) fb *= 2;
+    while (fb < 8 && fb * wo * (sc / 4) < 448 && 2 * (2 * fb) * plane <= 96 * 1024 && fb * 2 <= n) fb *= 2;
     const int stage_bytes = (int)(((size_t)fb * plane + 127) / 128 * 128);
     const size_t smem = (size_t)2 * stage_bytes + (size_t)10 * sc * 4 + (size_t)2 * fb * wo * sc * 4 + 16;
     EWVIT_REQUIRE(smem <= 200 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_dwconv3x3_nhwc_bf16: %dx%d needs %zu bytes of shared memory", h, wd, smem);
