@@ -675,7 +675,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ewvit::tc_fence_after();
             if (q == 2 && lane == 0) EWVIT_TRACE(2 + grp, it, 1);
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kBN);
-            if (kEpi == EPI_CONV) {
+            if (kEpi == EPI_CONV && (p.dbg & 512)) {
+                // debug: no epilogue work at all (isolates the MMA / operand-feed rate of the MWT convs)
+            } else if (kEpi == EPI_CONV) {
                 // MWT convs: the chunk loop is unrolled and software-pipelined -- the TMEM load of chunk c+1 is in flight while
                 // chunk c goes through BN + ReLU, packing, staging and its TMA store (320-thread kernel: registers to spare)
                 constexpr int kChunks = kColsPerGroup / 32;
