@@ -268,3 +268,26 @@ def test_forward_uint8_equals_forward_on_normalised_frames(detector):
     from ewvit import EwvitError
     with pytest.raises(EwvitError):
         detector.forward_uint8(xf.cuda(), 2)
+
+
+def test_other_dama_dims():
+    """dama_dim = 256 runs natively (two 128-wide column tiles per MWT conv; looser tolerance: the committed BatchNorm
+    calibration scalars are for the reference's default dim = 128); a dim the kernels do not tile raises loudly."""
+    from _weights import fill_module_
+    from ewvit import EwvitError
+    from network.model import DeepfakeDetector
+    torch.manual_seed(0)
+    m = DeepfakeDetector(3, 256, batch_size=2)
+    fill_module_(m, seed=0)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items() if k.startswith("dama.") or k.startswith("classifier.")}
+    m = m.cuda().eval()
+    x = seeded_randn((1, 2, 3, 224, 224), 5)
+    with torch.no_grad():
+        out = m(x.cuda(), 2, "dynamic")
+    ref = O.detector_forward(sd, x, 2, "dynamic")
+    for k in ("logits", "fused", "space", "freq"):
+        check(f"dim 256 [{k}]", out[k], ref[k], 6e-2)
+    m64 = DeepfakeDetector(3, 64, batch_size=2).cuda().eval()
+    with pytest.raises(EwvitError, match="multiple of 128"):
+        with torch.no_grad():
+            m64(x.cuda(), 2, "dynamic")
