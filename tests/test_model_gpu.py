@@ -291,3 +291,29 @@ def test_other_dama_dims():
     with pytest.raises(EwvitError, match="multiple of 128"):
         with torch.no_grad():
             m64(x.cuda(), 2, "dynamic")
+
+
+def test_training_step_focal_loss_accumulation():
+    """BASELINE configs[4], one rank: two accumulated micro-steps (forward + backward through the PyTorch composition with the
+    native Haar kernel and its adjoint, focal + orthogonality loss) and one Adam step.  Gradients reach the dynamic path
+    only (model.mwt / model.sfe / model.sfe_cls / model.fusion_gate stay untouched), the step moves the
+    weights and the result stays finite; afterwards the eval-mode native path serves the updated weights."""
+    from _weights import fill_module_
+    from ewvit.training import train_step
+    from network.model import DeepfakeDetector
+    torch.manual_seed(0)
+    m = DeepfakeDetector(3, 128, batch_size=2)
+    fill_module_(m, seed=0)
+    m = m.cuda().train()
+    opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4)
+    before = m.dama.mwt.multiscale_fusion[0].weight.detach().clone()
+    micro = [(seeded_randn((1, 2, 3, 224, 224), 60 + i).cuda(), torch.tensor([i], device="cuda")) for i in range(2)]
+    loss = train_step(m, micro, opt, batch_size=2, epoch=5, max_epochs=10)
+    assert loss == loss and abs(loss) < 1e4
+    assert m.dama.mwt.multiscale_fusion[0].weight.grad is not None and m.classifier[0].weight.grad is not None
+    assert m.mwt.multiscale_fusion[0].weight.grad is None and m.fusion_gate[0].weight.grad is None
+    assert not torch.equal(before, m.dama.mwt.multiscale_fusion[0].weight.detach())
+    m.eval()
+    with torch.no_grad():
+        out = m(micro[0][0], 2, "dynamic")
+    assert torch.isfinite(out["logits"]).all()
