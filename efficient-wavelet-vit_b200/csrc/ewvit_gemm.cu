@@ -93,7 +93,6 @@ struct GemmParams {
     // A_SCALED (1x1 conv behind a squeeze-excitation block): the A tile arrives by TMA as for A_FLAT and builder warps
     // multiply it in place by the per-(frame, channel) gate before the MMA consumes it, so the separate x *= gate
     // pass (one read + one write of the expanded tensor) disappears; tile geometry = A_FLAT
-    const __nv_bfloat16 *a_ptr;
     const void *a_gate;    // [frames, K] fp32, or bf16 when a_gate_bf16
     int a_gate_bf16;
     int a_hw;              // rows (pixels) per frame
@@ -1504,7 +1503,6 @@ extern "C" int ewvit_conv1x1_gated_nhwc_bf16(const void *x, const void *gate, in
     const int num_kb = (cin + BK - 1) / BK;
     GemmParams p = {};
     p.a_mode = A_SCALED;
-    p.a_ptr = static_cast<const __nv_bfloat16 *>(x);
     p.a_gate = gate;
     p.a_gate_bf16 = gate_bf16 ? 1 : 0;
     p.a_hw = hw;

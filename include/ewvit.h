@@ -298,8 +298,10 @@ EWVIT_API int ewvit_conv1x1_gated_nhwc_bf16(const void *x, const void *gate, int
  * clock64 stamps of its warp roles to this device buffer ([6 roles][64 tiles][4] int64).  NULL switches it off. */
 EWVIT_API int ewvit_debug_set_trace(void *device_buffer);
 
-/* Debug experiments on the tensor-core kernel's epilogue (bit 0: skip the global stores, bit 1: skip the
- * activation).  0 restores normal behaviour.  Never set in production. */
+/* Debug / A-B switches of the tensor-core kernel (tools/*.py use them to attribute time).  0 restores normal behaviour; never
+ * set in production.  1: generic backbone epilogue skips its global stores; 2: ... skips the activation; 32: MWT 3x3 convs
+ * fetch one tile per tap instead of row-shared windows; 64: no resident weights; 256: generic instead of specialised
+ * backbone epilogues; 512: MWT epilogue does no work at all. */
 EWVIT_API int ewvit_debug_set_flags(int flags);
 
 #ifdef __cplusplus
