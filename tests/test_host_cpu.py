@@ -118,3 +118,53 @@ def test_train_mode_torch_composition_matches_oracle_in_eval_math(model, manifes
         x = O.vit_tokens_from_features(sd, "dama.sfe.", feat)
         assert torch.allclose(model.dama.sfe.transformer(x), O.vit_transformer(sd, "dama.sfe.", x), atol=1e-4)
     model.train()
+
+
+def test_backbone_layout_plan_and_window_weight_packing():
+    """Host logic of the native EfficientNetV2-S runner (no kernels): which ops run on padded-flat tensors, and the weight
+    layout of the overlapping-window conv path (include/ewvit.h: k = dy*(nsub*64) + dx*cin + c)."""
+    from torchvision.models import efficientnet_v2_s
+    from ewvit import engine
+    torch.manual_seed(0)
+    net = efficientnet_v2_s(weights=None).eval()
+    nb = engine.NativeEffNetV2(net.features, "cpu")
+    kinds = [op[0] for op in nb.ops]
+    assert kinds[0] == "stem" and kinds.count("dw") == 30 and len(kinds) == 140
+    # stage-2 48->192 convs take the window path on padded tensors; the 24-channel stage-1 convs and everything from the
+    # stride-2 conv into stage 3 on stay on plain layouts
+    win = sorted(nb.win_w)
+    assert win == [5, 7, 9] and all(nb.layout[i] == (True, True) for i in win)
+    assert nb.layout[0] == (False, False) and nb.layout[1] == (False, False) and nb.layout[2] == (False, False)
+    assert nb.layout[3] == (False, True)          # stride-2 conv writes the padded layout the next 1x1 conv keeps
+    assert nb.layout[4] == (True, True) and nb.layout[10] == (True, True)
+    assert nb.layout[11] == (True, False)         # stride-2 conv reads the padded interior, writes a plain tensor
+    assert all(l == (False, False) for l in nb.layout[12:])
+    assert not any(a != b and kinds[i] not in ("stem", "conv3") for i, (a, b) in enumerate(nb.layout))
+    nb_plain = engine.NativeEffNetV2.__new__(engine.NativeEffNetV2)
+    nb_plain.__dict__.update(nb.__dict__)
+    assert nb_plain._plan_layouts(False) == [(False, False)] * len(nb.ops)
+    # SiLU convs carry pre-halved weights (exact) and the halved activation code
+    assert nb.ops[5][4] == "silu_h" and nb.ops[1][4] == "silu"          # 24->24 layers use the direct-conv kernel, not halved
+    w = torch.randn(192, 48, 3, 3)
+    pk = engine._w3x3_window_packed(w)
+    assert pk.shape == (192, 3 * 3 * 64) and pk.dtype == torch.bfloat16
+    for (oc, c, dy, dx) in ((0, 0, 0, 0), (5, 47, 2, 1), (191, 13, 1, 2)):
+        assert float(pk[oc, dy * 192 + dx * 48 + c]) == float(w[oc, c, dy, dx].bfloat16())
+    assert float(pk[:, 144:192].abs().max()) == 0.0 and float(pk[:, 192 + 144:384].abs().max()) == 0.0
+
+
+def test_mwt_head_block_diagonal_packing(model):
+    """The tensor-core head's [64, 192] matrix: w[18g+oc][dy*64 + dx*16 + 3g+ic] = seperate[g].weight[oc][ic][dy][dx]."""
+    from ewvit import engine
+    sd = {k[len("dama.mwt."):]: v.detach().float() for k, v in model.state_dict().items() if k.startswith("dama.mwt.")}
+    run = engine.MwtRunner.__new__(engine.MwtRunner)
+    try:
+        engine.MwtRunner.__init__(run, sd)
+    except Exception:
+        pytest.skip("MwtRunner needs CUDA tensors for its remaining packs")
+    wbd = run.head_wbd.float().view(64, 3, 4, 16)
+    for g in range(3):
+        wg = sd[f"hf_conv.seperate.{g}.0.weight"]
+        for (oc, ic, dy, dx) in ((0, 0, 0, 0), (17, 2, 2, 2), (9, 1, 1, 0)):
+            assert float(wbd[18 * g + oc, dy, dx, 3 * g + ic]) == float(wg[oc, ic, dy, dx].bfloat16())
+    assert float(wbd[54:].abs().max()) == 0.0 and float(wbd[:, :, 3].abs().max()) == 0.0
