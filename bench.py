@@ -17,7 +17,8 @@ public module call with pinned HOST frames (H2D copy + forward + D2H logits insi
 
 --impl reference : the reference's CPU implementation of the path.  The reference is pure Python and cannot travel
 to the GPU box, so this arm times the oracle port (oracle/ewvit_oracle.py, validated against the unmodified
-reference by tests/golden) on the host cores, each step a bounded sample (one video x 8 frames) of the workload.
+reference by tests/golden) on the host cores, each step a bounded sample of the SAME workload: one of its eight
+reference chunks (8 videos x 8 frames = 64 frames through `_process_frame`, dama.py:179-186).
 """
 import argparse
 import json
@@ -32,6 +33,8 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(REPO, "efficient-wavelet-vit_b200"))
 sys.path.insert(0, REPO)
 
+os.environ.setdefault("EWVIT_ALLOW_RANDOM_BACKBONE", "1")      # random-init weights are the benchmark's definition (BASELINE.json)
+
 import torch  # noqa: E402
 
 VIDEOS, FRAMES, BATCH_SIZE, SIDE = 8, 64, 8, 224
@@ -41,8 +44,8 @@ METRIC = "frames/sec EWViT forward 224x224 (dynamic mode, bf16, batch 512 frames
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)          # ~2 s timed region: comparable with the sustained peak figures
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (debug)")
     return ap.parse_args()
@@ -52,7 +55,7 @@ def workload_config(n_gpus):
     return {"workload": "configs[2]: full EWViT inference, ablation=dynamic, 8 videos x 64 frames x 3x224x224 per GPU, "
                         "batch_size=8 (reference chunks of 64 frames), random-init weights seed 42",
             "frames_per_gpu_per_step": VIDEOS * FRAMES, "global_frames_per_step": VIDEOS * FRAMES * n_gpus,
-            "parallelism": f"dp{n_gpus} (videos sharded by rank, NCCL all_gather of logits)" if n_gpus > 1 else "single GPU",
+            "parallelism": f"dp{n_gpus} (videos sharded by rank, one NCCL all_gather of all scores after the last step)" if n_gpus > 1 else "single GPU",
             "l2_policy": "inputs+activations per step (~9 GB) exceed the 126 MB L2; no explicit flush"}
 
 
@@ -103,26 +106,59 @@ def oracle_state_dict(model):
             if k.startswith("dama.") or k.startswith("classifier.")}
 
 
+CPU_SAMPLE = ("one reference chunk of configs[2]: x[8 videos, 8 frames, 3, 224, 224], batch_size 8 -> 64 frames through "
+              "_process_frame (1/8 of the GPU step's 512 frames), fp32, eval, oracle/ewvit_oracle.py")
+
+
 def time_cpu_oracle(sd, steps, warmup, budget_s=30.0):
-    """Oracle port on the host cores: x[1, 8, 3, 224, 224], batch_size 8 (BASELINE.json configs[0])."""
+    """Oracle port on the host cores on a bounded sample of the benchmark workload: one of the eight 64-frame chunks the
+    reference would run for configs[2] (DAMA.forward chunk loop, dama.py:179-186)."""
     from oracle import ewvit_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    x = torch.randn(1, 8, 3, SIDE, SIDE, generator=torch.Generator().manual_seed(42))
+    x = torch.randn(VIDEOS, BATCH_SIZE, 3, SIDE, SIDE, generator=torch.Generator().manual_seed(42))
+    frames = VIDEOS * BATCH_SIZE
     for _ in range(max(1, warmup)):
-        O.detector_forward(sd, x, 8, "dynamic")
+        O.detector_forward(sd, x, BATCH_SIZE, "dynamic")
     times = []
     t_begin = time.perf_counter()
     for _ in range(steps):
         t0 = time.perf_counter()
-        O.detector_forward(sd, x, 8, "dynamic")
+        O.detector_forward(sd, x, BATCH_SIZE, "dynamic")
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_begin > budget_s:
             break
     mean = sum(times) / len(times)
-    return {"value": 8.0 / mean, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{len(times)} timed forwards of 1 video x 8 frames (batch_size 8, fp32, eval) through oracle/ewvit_oracle.py",
-            "ms_per_sample": mean * 1e3}
+    return {"value": frames / mean, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} timed passes of {CPU_SAMPLE}", "ms_per_sample": mean * 1e3, "frames_per_sample": frames}
+
+
+def time_gpu_eager(sd, dev, reps=3):
+    """INFORMATIONAL, not the target and not the product: the same oracle port (stock PyTorch ops: cuDNN convs, cuBLAS
+    GEMMs, ATen glue) run on the GPU -- what the unmodified reference's eager path does on this box (SURVEY.md section 2:
+    'the bar is the stock PyTorch eager path on the same box').  fp32 (TF32 off, the oracle's arithmetic) and bf16 autocast.
+    Same workload, chunk by chunk as the reference loops (8 chunks of 64 frames)."""
+    from oracle import ewvit_oracle as O
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    x = torch.randn(VIDEOS, FRAMES, 3, SIDE, SIDE, generator=torch.Generator().manual_seed(42)).to(dev)
+    out = {}
+    for name, ctx in (("fp32", torch.autocast("cuda", enabled=False)), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        with ctx:
+            O.detector_forward(sd_dev, x, BATCH_SIZE, "dynamic")
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                O.detector_forward(sd_dev, x, BATCH_SIZE, "dynamic")
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {"value": VIDEOS * FRAMES / ms * 1e3, "unit": "frames/s", "ms_per_step": ms}
+    out["note"] = ("informational only: oracle port (stock PyTorch eager, cuDNN/cuBLAS) on the same GPU, same 512-frame workload "
+                   "in the reference's 8 serial chunks; not the optimisation target, never part of the product path")
+    del sd_dev
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference_arm(args):
@@ -144,6 +180,30 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------- native arm
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and therefore its pinned host buffers, first-touch) to the CPUs of the NUMA node the GPU hangs off:
+    with 8 ranks each streaming 308 MB per step the H2D copies otherwise cross the socket interconnect.  Best effort."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"node": node, "cpus": len(allowed)}
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    return None
+
+
 def load_peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -194,15 +254,27 @@ def main():
     sd_cpu = oracle_state_dict(model) if rank == 0 else None
     model = model.to(dev).eval()
 
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None       # before the pinned allocations: first touch puts them on the GPU's node
     gen = torch.Generator().manual_seed(1000 + rank)
     x_host = torch.randn(VIDEOS, FRAMES, 3, SIDE, SIDE, generator=gen).pin_memory()
     x_dev = x_host.to(dev, non_blocking=True)
-    gathered = [torch.empty(VIDEOS, 1, device=dev) for _ in range(world)] if world > 1 else None
+    # per-step logits of this rank land in one device buffer; ONE NCCL all_gather at the end of the timed steps collects
+    # every rank's scores ("the final logit gather" of north_star): no per-step collective, ranks never wait for each other
+    score_buf = torch.empty(max(args.steps, args.warmup, 3) + 2, VIDEOS, device=dev)
+    gathered = torch.empty(world, *score_buf.shape, device=dev) if world > 1 else None
+    step_no = {"i": 0}
+
+    def keep_scores(logits):
+        score_buf[step_no["i"] % score_buf.shape[0]].copy_(logits.view(-1))
+        step_no["i"] += 1
+
+    def final_gather():
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, score_buf)
 
     def step_resident():
         out = model(x_dev, BATCH_SIZE, "dynamic")
-        if world > 1:
-            dist.all_gather(gathered, out["logits"])
+        keep_scores(out["logits"])
         return out["logits"]
 
     # e2e: pinned host frames -> device -> forward -> logits back to the host, every step.  Two device staging
@@ -231,8 +303,7 @@ def main():
         torch.cuda.current_stream().wait_event(copied[slot])
         out = model(x_stage[slot], BATCH_SIZE, "dynamic")
         consumed[slot].record()
-        if world > 1:
-            dist.all_gather(gathered, out["logits"])
+        keep_scores(out["logits"])
         logits_host.copy_(out["logits"], non_blocking=True)      # D2H of the step's result
         e2e_state["i"] = i + 1
         return logits_host
@@ -248,6 +319,7 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        final_gather()                       # inside the timed region
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -304,8 +376,7 @@ def main():
             torch.cuda.current_stream().wait_event(copied[slot])
             out = model.forward_uint8(u8_stage[slot], BATCH_SIZE)
             consumed[slot].record()
-            if world > 1:
-                dist.all_gather(gathered, out["logits"])
+            keep_scores(out["logits"])
             logits_host.copy_(out["logits"], non_blocking=True)
             u8_state["i"] = i + 1
             return logits_host
@@ -383,7 +454,11 @@ def main():
                                     "ms_per_launch": dwt[1], "workload": "256x3x224x224 fp32, LL1-3 + HF1-3 written",
                                     "timing": "median over 5 replays of a CUDA graph holding 20 launches"},
     }
-    cpu = None if args.no_cpu_baseline else time_cpu_oracle(sd_cpu, 8, 1, budget_s=25.0)
+    cpu = eager = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu = time_cpu_oracle(sd_cpu, 12, 1, budget_s=25.0)
+        with torch.no_grad():
+            eager = time_gpu_eager(sd_cpu, dev)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -393,7 +468,8 @@ def main():
         "e2e_uint8_input": {"value": world * n_frames * args.steps / (e2e_u8_ms / 1e3), "unit": "frames/s",
                             "h2d_bytes_per_step": u8_host.numel(), "d2h_bytes_per_step": VIDEOS * 4, "ms_per_step": e2e_u8_ms / args.steps,
                             "note": "extension (SURVEY 8f-3): model.forward_uint8, ToTensor+Normalize fused into the DWT and stem kernels"},
-        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, **extra,
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "numa_binding": numa,
+        **extra,
     }
     print(json.dumps(line))
     if world > 1:

@@ -13,12 +13,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 // x[n,0,:] = cls + pos[idx[n]] ; x[n,1,:] = emb[n] + pos[idx[n]]      (sfe.py:156-159)
 __global__ void vit_assemble_kernel(const float *__restrict__ emb, const float *__restrict__ cls,
                                     const float *__restrict__ pos, const int *__restrict__ pos_index, float *__restrict__ x,
-                                    long long n, int d) {
+                                    long long n, int d, int pos_rows) {
     const long long total = n * d;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long f = i / d;
         const int c = (int)(i % d);
-        const float pe = pos[(long long)pos_index[f] * d + c];
+        const int pi = pos_index[f];
+        // an index outside the table (the reference's broadcast raises, sfe.py:158-159; the host wrappers check first)
+        // poisons the frame's tokens instead of reading out of bounds
+        const float pe = (unsigned)pi < (unsigned)pos_rows ? pos[(long long)pi * d + c] : __int_as_float(0x7fc00000);
         x[(f * 2) * d + c] = cls[c] + pe;
         x[(f * 2 + 1) * d + c] = emb[f * d + c] + pe;
     }
@@ -105,7 +108,7 @@ extern "C" int ewvit_vit_assemble(const float *emb, const float *cls, const floa
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)ewvit_num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    vit_assemble_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(emb, cls, pos, pos_index, x, n, d);
+    vit_assemble_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(emb, cls, pos, pos_index, x, n, d, pos_rows);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }

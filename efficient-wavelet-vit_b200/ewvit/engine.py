@@ -90,6 +90,24 @@ def _sub(sd, prefix):
     return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
 
 
+def _host_sd(sd):
+    """(CPU copies of the state-dict tensors, device they live on).  Every runner folds / re-lays-out its weights on the
+    HOST (a few ms of fp32 CPU math on <= 61 M parameters) and uploads the results once: a rebuild after load_state_dict
+    or an optimizer step costs two memcpys per tensor instead of ~10 tiny elementwise launches per layer."""
+    dev = next(iter(sd.values())).device
+    return {k: v.detach().to("cpu") for k, v in sd.items()}, dev
+
+
+def _to_device(obj, dev):
+    if torch.is_tensor(obj):
+        return obj.to(dev)
+    if isinstance(obj, dict):
+        return {k: _to_device(v, dev) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_to_device(v, dev) for v in obj)
+    return obj
+
+
 # ------------------------------------------------------------------------------------------ MWT
 class MwtRunner:
     """Native ``MWT.forward`` (levels = 3, in_channels = 3).  ``sd`` holds the module's own keys
@@ -103,8 +121,8 @@ class MwtRunner:
         if levels != 3:
             raise EwvitError("native MWT implements the reference's 3-level decomposition (model.py:35) only")
         self.dim, self.levels = dim, levels
-        dev = sd["freq_conv.0.weight"].device
-        self.device = dev
+        sd, target = _host_sd(sd)
+        dev = torch.device("cpu")
         # hf_conv.seperate: three Conv2d(3,18)+BN, stacked
         self.head_w = torch.stack([sd[f"hf_conv.seperate.{i}.0.weight"].float() for i in range(3)]).contiguous()
         sc, sh = zip(*[_fold_bn(sd, f"hf_conv.seperate.{i}.0.", f"hf_conv.seperate.{i}.1.") for i in range(3)])
@@ -119,8 +137,6 @@ class MwtRunner:
         self.head_shift64 = torch.zeros(64, dtype=torch.float32, device=dev)
         self.head_scale64[:54] = self.head_scale
         self.head_shift64[:54] = self.head_shift
-        import os
-        self.head_mode = os.environ.get("EWVIT_HEAD", "tc")        # tc (default: upsample + tcgen05 conv) | mma (one warp-MMA kernel, same speed) | simt (fp32 CUDA cores)
         self.fus_w = _conv_w_tapmajor(sd["hf_conv.fusion.0.weight"], 64)
         self.fus_scale, self.fus_shift = _fold_bn(sd, "hf_conv.fusion.0.", "hf_conv.fusion.1.")
         self.ms_w = _conv_w_tapmajor(sd["multiscale_fusion.0.weight"])
@@ -129,19 +145,26 @@ class MwtRunner:
         self.fc_scale, self.fc_shift = _fold_bn(sd, "freq_conv.0.", "freq_conv.1.")
         self.fp_w = _conv_w_tapmajor(sd["freq_pool.1.weight"])
         self.fp_scale, self.fp_shift = _fold_bn(sd, "freq_pool.1.", "freq_pool.2.")
+        self.__dict__.update(_to_device(self.__dict__, target))
+        self.device = target
         self._ws = {}
 
     def _workspace(self, n, h, w):
-        key = (n, h, w)
-        ws = self._ws.get(key)
-        if ws is None:
-            if len(self._ws) > 4:
+        """One grow-only workspace per frame size (~17 MB per frame): allocated for the largest n seen, smaller batches
+        (ragged tails of the macro-batch splitter) use leading slices.  Single-stream: two concurrent forwards of one
+        runner on different CUDA streams would share these buffers."""
+        full = self._ws.get((h, w))
+        if full is None or full["n"] < n:
+            self._ws.pop((h, w), None)
+            full = None
+            if len(self._ws) > 1:           # a third frame size: drop the others rather than hold several multi-GB sets
                 self._ws.clear()
             dev, bf = self.device, torch.bfloat16
             h1, w1, d = h // 2, w // 2, self.dim
             h2, w2 = (h1 - 1) // 2 + 1, (w1 - 1) // 2 + 1          # freq_conv, stride 2
             h4, w4 = (h2 // 2 - 1) // 2 + 1, (w2 // 2 - 1) // 2 + 1  # maxpool then stride-2 conv
-            ws = {
+            full = {
+                "n": n,
                 "hf": [torch.empty((n, 3, 3, h >> l, w >> l), dtype=torch.float32, device=dev) for l in (1, 2, 3)],
                 "up": torch.zeros((n, h1 + 2, w1 + 2, 16), dtype=bf, device=dev),        # zero border, kept zero
                 "head": torch.zeros((n, h1 + 2, w1 + 2, 64), dtype=bf, device=dev),      # zero border, kept zero
@@ -151,8 +174,10 @@ class MwtRunner:
                 "mp": torch.empty((n, h2 // 2, w2 // 2, d), dtype=bf, device=dev),
                 "pc": torch.empty((n, h4, w4, d), dtype=bf, device=dev),
             }
-            self._ws[key] = ws
-        return ws
+            self._ws[(h, w)] = full
+        if full["n"] == n:
+            return full
+        return {k: ([t[:n] for t in v] if isinstance(v, list) else v[:n]) for k, v in full.items() if k != "n"}
 
     def forward(self, frames, out=None, norm=None):
         """frames [n,3,H,W] fp32 CUDA (or uint8 with norm=(mean, std)), H, W multiples of 8 -> [n, dim] fp32."""
@@ -167,11 +192,8 @@ class MwtRunner:
         for lvl in range(3):
             with stage("mwt.head"):
                 hfl = hf[lvl].view(n, 9, h >> (lvl + 1), w >> (lvl + 1))
-                if self.head_mode == "tc":
-                    ops.mwt_upsample(hfl, ws["up"], h1, w1)
-                    ops.mwt_head_conv(ws["up"], self.head_wbd, self.head_scale64, self.head_shift64, ws["head"], h1, w1)
-                else:
-                    ops.mwt_head(hfl, self.head_w, self.head_scale, self.head_shift, ws["head"], h1, w1, mma=self.head_mode == "mma")
+                ops.mwt_upsample(hfl, ws["up"], h1, w1)
+                ops.mwt_head_conv(ws["up"], self.head_wbd, self.head_scale64, self.head_shift64, ws["head"], h1, w1)
             with stage("mwt.hf_fusion"):
                 ops.conv3x3_bf16(ws["head"], self.fus_w, n, h1, w1, 1, True, self.fus_scale, self.fus_shift, True,
                                  ws["cat"], lvl * d, True)
@@ -189,10 +211,8 @@ class MwtRunner:
 
 # ------------------------------------------------------------------------------------------ SFE
 def make_backbone(features: nn.Module, device, v2s: bool):
-    """V2-S (torchvision) -> native kernels; anything else (the b0 ablation branches), or EWVIT_BACKBONE=cudnn ->
-    the cuDNN bf16 channels-last copy."""
-    import os
-    if v2s and os.environ.get("EWVIT_BACKBONE", "native") != "cudnn":
+    """V2-S (torchvision) -> native kernels; anything else (the b0 ablation branches) -> the cuDNN bf16 channels-last copy."""
+    if v2s:
         return NativeEffNetV2(features, device)
     return fused_bf16_backbone(features, device)
 
@@ -252,12 +272,13 @@ class NativeEffNetV2:
     scaling in one kernel; the stem reads the fp32 NCHW frames directly.  NHWC bf16 activations, BatchNorm folded."""
 
     def __init__(self, features: nn.Module, device):
-        import os
-        dev = torch.device(device)
-        self.device = dev
+        target = torch.device(device)
+        dev = torch.device("cpu")           # fold and pack on the host, upload once at the end
+        if any(p.device.type != "cpu" for p in features.parameters()):
+            features = copy.deepcopy(features).to("cpu")
         self.ops = []
-        self.fuse_se = os.environ.get("EWVIT_SE_FUSED", "1") == "1"
-        self.c24 = os.environ.get("EWVIT_C24_DIRECT", "1") == "1"
+        self.fuse_se = True         # SE gate applied inside the project conv's operand path
+        self.c24 = True             # 24 -> 24 stage-1 convs on the direct warp-MMA kernel
         self.win_w, self.cin3 = {}, {}      # op index -> window-packed weights / input channels of the 3x3 convs
         self._padbuf = {}
         mods = list(features)
@@ -307,7 +328,7 @@ class NativeEffNetV2:
         head = mods[-1]
         w, b = _fold_conv_bn(head[0], head[1])
         self.ops.append(("conv1", w.flatten(1).to(torch.bfloat16).to(dev).contiguous(), b.to(dev), "silu", False, False))
-        self.layout = self._plan_layouts(os.environ.get("EWVIT_WINDOW_CONV", "1") == "1")
+        self.layout = self._plan_layouts(True)
         # SiLU epilogues evaluate h*tanh(h) + h with h = v/2: fold the 1/2 into weights and bias (exact: a power of two)
         for i, op in enumerate(self.ops):
             if op[0] == "conv3" and op[4] == "silu" and not self._is_c24(i):
@@ -316,6 +337,9 @@ class NativeEffNetV2:
                     self.win_w[i] = self.win_w[i] * 0.5
             elif op[0] == "conv1" and op[3] == "silu":
                 self.ops[i] = ("conv1", op[1] * 0.5, op[2] * 0.5, "silu_h", op[4], op[5])
+        self.ops = _to_device(self.ops, target)
+        self.win_w = _to_device(self.win_w, target)
+        self.device = target
 
     def _is_c24(self, i):
         op = self.ops[i]
@@ -359,15 +383,16 @@ class NativeEffNetV2:
         return plain if padded else plan
 
     def _zero_bordered(self, i, shape):
-        """Persistent output buffer of op i whose border is zeroed once (the op rewrites the interior every call)."""
-        key = (i, shape)
+        """Persistent output buffer of op i whose border is zeroed once (the op rewrites the interior every call).
+        Grow-only in the frame count; smaller batches use a leading slice."""
+        key = (i, tuple(shape[1:]))
         t = self._padbuf.get(key)
-        if t is None:
+        if t is None or t.shape[0] < shape[0]:
             if len(self._padbuf) > 16:
                 self._padbuf.clear()
             t = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
             self._padbuf[key] = t
-        return t
+        return t[: shape[0]]
 
     def forward(self, frames, norm=None):
         """fp32 [n,3,H,W] (or uint8 with norm=(mean, std)) -> bf16 NHWC [n, H/32, W/32, C_out]."""
@@ -439,7 +464,7 @@ class SfeRunner:
         self.dim, self.depth, self.heads, self.dim_head = m["dim"], m["depth"], m["heads"], m["dim-head"]
         self.mlp_dim, self.emb_dim = m["mlp-dim"], m["emb-dim"]
         self.output_mode = output_mode
-        self.backbone = backbone
+        sd, target = _host_sd(sd)
         bf = torch.bfloat16
         f32 = lambda k: sd[k].float().contiguous()
         self.patch_w = sd["patch_to_embedding.weight"].to(bf).contiguous()
@@ -476,30 +501,37 @@ class SfeRunner:
             pad = (-fw.shape[0]) % 128
             self.fm_w = torch.cat([fw.to(bf), torch.zeros((pad, fw.shape[1]), dtype=bf, device=fw.device)]).contiguous()
             self.fm_b = torch.cat([sd["feat_map.0.bias"].float(), torch.zeros(pad, device=fw.device)]).contiguous()
+        self.__dict__.update(_to_device(self.__dict__, target))
+        self.backbone = backbone
         self._ws = {}
 
     def _workspace(self, n, dev):
-        ws = self._ws.get(n)
-        if ws is None:
-            if len(self._ws) > 4:
-                self._ws.clear()
+        """Grow-only token workspace (largest n seen; smaller batches use leading slices)."""
+        inner = self.heads * self.dim_head
+        kblocks = self.patch_w.shape[1] // 64
+        splits = max(1, min(kblocks, 148 // max(1, math.ceil(n / 128) * (self.dim // 128))))
+        full = self._ws
+        if not full or full["n"] < n or full["dev"] != dev:
             f32, bf = torch.float32, torch.bfloat16
-            inner = self.heads * self.dim_head
-            kblocks = self.patch_w.shape[1] // 64
-            splits = max(1, min(kblocks, 148 // max(1, math.ceil(n / 128) * (self.dim // 128))))
-            ws = {
-                "splits": splits,
-                "ws": torch.empty((splits, n, self.dim), dtype=f32, device=dev) if splits > 1 else None,
-                "emb": torch.empty((n, self.dim), dtype=f32, device=dev),
-                "x": [torch.empty((2 * n, self.dim), dtype=f32, device=dev) for _ in range(2)],
-                "xn": torch.empty((2 * n, self.dim), dtype=bf, device=dev),
-                "qkv": torch.empty((2 * n, 3 * inner), dtype=f32, device=dev),
-                "att": torch.empty((2 * n, inner), dtype=bf, device=dev),
-                "hid": torch.empty((2 * n, self.mlp_dim), dtype=bf, device=dev),
-                "tok": torch.empty((n, self.dim), dtype=bf, device=dev),
+            cap = max(n, 64)
+            max_splits = max(1, min(kblocks, 148 // max(1, self.dim // 128)))
+            full = self._ws = {
+                "n": cap, "dev": dev,
+                "ws": torch.empty((max_splits * cap * self.dim,), dtype=f32, device=dev),
+                "emb": torch.empty((cap, self.dim), dtype=f32, device=dev),
+                "x": [torch.empty((2 * cap, self.dim), dtype=f32, device=dev) for _ in range(2)],
+                "xn": torch.empty((2 * cap, self.dim), dtype=bf, device=dev),
+                "qkv": torch.empty((2 * cap, 3 * inner), dtype=f32, device=dev),
+                "att": torch.empty((2 * cap, inner), dtype=bf, device=dev),
+                "hid": torch.empty((2 * cap, self.mlp_dim), dtype=bf, device=dev),
+                "tok": torch.empty((cap, self.dim), dtype=bf, device=dev),
             }
-            self._ws[n] = ws
-        return ws
+        return {
+            "splits": splits,
+            "ws": full["ws"][: splits * n * self.dim].view(splits, n, self.dim) if splits > 1 else None,
+            "emb": full["emb"][:n], "x": [t[: 2 * n] for t in full["x"]], "xn": full["xn"][: 2 * n],
+            "qkv": full["qkv"][: 2 * n], "att": full["att"][: 2 * n], "hid": full["hid"][: 2 * n], "tok": full["tok"][:n],
+        }
 
     def head(self, feat_nhwc, pos_index, out=None):
         """feat_nhwc: bf16 [n, ph*pw*channels] (NHWC flatten of the backbone map); pos_index int32 [n]."""
@@ -556,6 +588,7 @@ class SfeRunner:
 def pack_dama_weights(sd, dim, depth=2):
     """Flatten the cross-attention / gate weights into the layout of ``ewvit_dama_tail_fwd`` (include/ewvit.h)."""
     parts = []
+    sd, target = _host_sd({k: v for k, v in sd.items() if k.startswith(("cross_att.", "fusion_gate.", "gate_net."))})
     f = lambda k: sd[k].float()
     for l in range(depth):
         for ln, att in ((0, 1), (2, 3)):
@@ -567,7 +600,7 @@ def pack_dama_weights(sd, dim, depth=2):
     parts += [centre.t(), scale, shift, f("gate_net.2.weight").t(), f("gate_net.2.bias"), f("gate_net.5.weight"), f("gate_net.5.bias")]
     pack = torch.cat([p.contiguous().reshape(-1) for p in parts]).contiguous()
     assert pack.numel() == ops.dama_wpack_floats(dim, depth)
-    return pack
+    return pack.to(target)
 
 
 def chunk_pos_index(b, k, batch_size):
@@ -600,9 +633,6 @@ class DamaRunner:
         self.mwt = MwtRunner(_sub(sd, "mwt."), dim=dim, levels=levels)
         self.wpack = pack_dama_weights(sd, dim, depth)
         self._pos_cache = {}
-        self.side_stream = None
-        import os
-        self.overlap = os.environ.get("EWVIT_OVERLAP", "0") == "1"   # measured: no gain (every GEMM CTA fills an SM)
 
     def pos_index(self, b, k, batch_size, device):
         key = (b, k, batch_size, str(device))
@@ -616,27 +646,15 @@ class DamaRunner:
 
     def process_frames(self, frames, pos_index, norm=None):
         """frames [n,3,H,W] -> (fused, space, freq) each [n, dim] fp32 (``_process_frame``, dama.py:130-169)."""
-        if self.overlap and TIMER is None:
-            # the two branches are independent until the fusion tail: run the frequency branch on a side stream so
-            # its kernels fill the tails / launch gaps of the ~170 short backbone kernels (and vice versa)
-            if self.side_stream is None:
-                self.side_stream = torch.cuda.Stream(device=frames.device)
-            main = torch.cuda.current_stream()
-            self.side_stream.wait_stream(main)
-            with torch.cuda.stream(self.side_stream):
-                freq = self.mwt.forward(frames, norm=norm)
-            space = self.sfe.forward(frames, pos_index, norm=norm)
-            main.wait_stream(self.side_stream)
-        else:
-            space = self.sfe.forward(frames, pos_index, norm=norm)
-            freq = self.mwt.forward(frames, norm=norm)
+        space = self.sfe.forward(frames, pos_index, norm=norm)
+        freq = self.mwt.forward(frames, norm=norm)
         with stage("dama.tail"):
             return ops.dama_tail(space, freq, self.wpack, self.heads, self.depth, LN_EPS)
 
     def forward_frames(self, x, batch_size, norm=None):
         """x [B,K,3,H,W] fp32 CUDA (or uint8 with norm=(mean, std)) -> per-frame (fused, space, freq) [B*K, dim] in (b, k) order."""
         b, k = x.shape[:2]
-        check_chunk_limit(b, k, batch_size, self.sfe.emb_dim)
+        check_chunk_limit(b, k, batch_size, self.sfe.pos.shape[0])      # rows of the checkpoint's pos_embedding, not the yaml's
         frames = x.reshape(b * k, *x.shape[2:])
         if not frames.is_contiguous():
             frames = frames.contiguous()
@@ -658,7 +676,7 @@ class DetectorRunner:
 
     def __init__(self, sd, cfg, backbone, dim=128):
         self.dama = DamaRunner(_sub(sd, "dama."), cfg, backbone, dim=dim)
-        f = lambda k: sd[k].float().contiguous()
+        f = lambda k: sd[k].detach().float().contiguous()
         self.classifier = (f("classifier.0.weight"), f("classifier.0.bias"), f("classifier.3.weight").reshape(-1).contiguous(),
                            f("classifier.3.bias"))
 

@@ -112,9 +112,15 @@ class EfficientNet(nn.Module):
     def from_pretrained(cls, model_name, **kwargs):
         if model_name != "efficientnet-b0":
             raise NotImplementedError("only efficientnet-b0 is on the reference's path (sfe.py:109)")
-        return cls(**kwargs)       # no network: random init instead of the ImageNet download
+        net = cls(**kwargs)        # this stand-in has no weight source: random init (network/sfe.py warns about it)
+        net._ewvit_random_init = True
+        return net
 
-    from_name = from_pretrained
+    @classmethod
+    def from_name(cls, model_name, **kwargs):
+        if model_name != "efficientnet-b0":
+            raise NotImplementedError("only efficientnet-b0 is on the reference's path (sfe.py:109)")
+        return cls(**kwargs)
 
     def extract_features(self, x):
         x = F.silu(self._bn0(self._conv_stem(x)))

@@ -17,21 +17,19 @@ def load_architecture_config():
     raise FileNotFoundError("config/architecture.yaml")
 
 
-def force_torch_path():
-    return os.environ.get("EWVIT_FORCE_TORCH", "0") == "1"
-
-
 class NativeMixin:
-    """Caches a native runner per module; rebuilt whenever a parameter/buffer was modified in place,
-    replaced, or moved (sum of tensor versions + identities + device)."""
+    """Caches a native runner per module.  The runner holds re-laid-out COPIES of the weights (folded BatchNorm, bf16,
+    tap-major), so it is rebuilt whenever a parameter/buffer on the path was modified in place, replaced or moved:
+    the cache key lists (key, data_ptr, version counter, device) per tensor, and every ``train()``/``eval()`` transition
+    and every ``load_state_dict`` drops it.  One write path is invisible to all of that: ``p.data.copy_()`` /
+    ``p.data.fill_()`` bump neither the version nor the pointer (EMA/SWA swaps, ``vector_to_parameters``); after such a
+    write in eval mode call ``invalidate_native_cache()`` (or toggle ``train()``/``eval()``)."""
+
+    def _native_tensors(self):
+        return self.state_dict(keep_vars=True).items()
 
     def _native_signature(self):
-        sig = 0
-        dev = None
-        for t in self.state_dict(keep_vars=True).values():
-            sig += t._version + (id(t) & 0xFFFF)
-            dev = t.device
-        return sig, str(dev)
+        return tuple((k, t.data_ptr(), t._version, str(t.device)) for k, t in self._native_tensors())
 
     def _native_runner(self, build):
         sig = self._native_signature()
@@ -43,20 +41,45 @@ class NativeMixin:
         return cache[1]
 
     def invalidate_native_cache(self):
+        """Drop the native runner of this module and of every native sub-module."""
+        for m in self.modules():
+            m.__dict__.pop("_ewvit_cache", None)
+
+    def train(self, mode=True):
+        self.__dict__.pop("_ewvit_cache", None)          # nn.Module.train recurses, so sub-modules drop theirs too
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *args, **kwargs):
         self.__dict__.pop("_ewvit_cache", None)
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def _use_native(self, x):
-        """Native kernels serve eval-mode CUDA calls.  Training (autograd, BatchNorm batch statistics,
-        dropout) and calls with forward hooks installed on sub-modules take the PyTorch composition."""
-        if self.training or force_torch_path():
-            return False
-        if torch.is_grad_enabled() and x.requires_grad:      # gradients w.r.t. the input were asked for
+        """Native kernels serve eval-mode CUDA calls that need no autograd graph.  Training (BatchNorm batch statistics,
+        dropout), calls that need gradients (grad mode on and the input or any parameter on the path requires grad: the
+        native outputs carry no ``grad_fn``) and calls with forward hooks installed on sub-modules take the PyTorch
+        composition of the same modules."""
+        if self.training:
             return False
         if not x.is_cuda:
             from ewvit import EwvitError
             raise EwvitError(f"{type(self).__name__}: eval-mode forward needs CUDA tensors on a B200 "
                              "(the native path has no CPU fallback)")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            _warn_grad_mode_once(type(self).__name__)
+            return False
         for m in self.modules():
             if m._forward_hooks or m._forward_pre_hooks:
                 return False
         return True
+
+
+_WARNED = set()
+
+
+def _warn_grad_mode_once(name):
+    if name not in _WARNED:
+        _WARNED.add(name)
+        import warnings
+        warnings.warn(f"{name}: eval-mode forward with autograd enabled and trainable parameters builds a graph through the "
+                      "PyTorch composition; wrap inference in torch.no_grad() (as eval.py:149 does) to run the native "
+                      "sm_100a kernels", stacklevel=3)

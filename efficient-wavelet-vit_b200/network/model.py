@@ -43,14 +43,9 @@ class DeepfakeDetector(NativeMixin, nn.Module):
               if (k.startswith("dama.") and not k.startswith("dama.sfe.efficient_net.")) or k.startswith("classifier.")}
         return DetectorRunner(sd, self.config, backbone, dim=self.dama_dim)
 
-    def _native_signature(self):
+    def _native_tensors(self):
         # only the tensors the dynamic path reads decide when its runner is rebuilt
-        sig, dev = 0, None
-        for k, t in self.state_dict(keep_vars=True).items():
-            if k.startswith("dama.") or k.startswith("classifier."):
-                sig += t._version + (id(t) & 0xFFFF)
-                dev = t.device
-        return sig, str(dev)
+        return [(k, t) for k, t in self.state_dict(keep_vars=True).items() if k.startswith("dama.") or k.startswith("classifier.")]
 
     def forward(self, x, batch_size, ablation):
         if batch_size is not None:
@@ -86,7 +81,8 @@ class DeepfakeDetector(NativeMixin, nn.Module):
         The reference's input pipeline turns decoded frames into floats with ``ToTensor`` and ``Normalize(mean, std)``
         (config/transforms.py:97-98) on the host; here that arithmetic happens on load inside the first two kernels (fused
         DWT, backbone stem), so a quarter of the bytes cross PCIe and HBM.  Bit-identical to
-        ``forward(((x.float() / 255) - mean) / std, batch_size, 'dynamic')``.  Eval mode, CUDA, dynamic ablation only."""
+        ``forward(((x.float() / 255) - mean) / std, batch_size, 'dynamic')`` under ``torch.no_grad()``.  Eval mode, CUDA, dynamic
+        ablation only; inference only (the outputs never carry a ``grad_fn``); ``self.ablation`` is left alone."""
         from ewvit import EwvitError
         if x.dtype != torch.uint8 or x.dim() != 5 or x.shape[2] != 3:
             raise EwvitError("forward_uint8: x must be a uint8 tensor [B, K, 3, H, W]")
@@ -100,7 +96,6 @@ class DeepfakeDetector(NativeMixin, nn.Module):
         if norm is None:        # built once: a host -> device copy per call would serialise the caller's copy/compute overlap
             norm = (torch.tensor(key[1], dtype=torch.float32, device=x.device), torch.tensor(key[2], dtype=torch.float32, device=x.device))
             cache[key] = norm
-        self.ablation = "dynamic"
         return self._native_runner(self._build_runner).forward(x.contiguous(), self.batch_size, norm=norm)
 
     def configure_ablation(self, ablation):

@@ -97,6 +97,9 @@ class EfficientViT(NativeMixin, nn.Module):
 
         if selected_efficient_net == 0:
             self.efficient_net = EfficientNet.from_pretrained("efficientnet-b0")
+            if getattr(self.efficient_net, "_ewvit_random_init", False) and os.environ.get("EWVIT_ALLOW_RANDOM_BACKBONE", "0") != "1":
+                _warn_random_backbone("EfficientNet-b0 (efficientnet_pytorch is not installed; built-in architecture copy)",
+                                      ImportError("no pretrained source"))
         else:
             self.efficient_net = efficientnet_v2_s(weights=_v2s_weights())
             self.efficient_net.classifier = nn.Identity()
@@ -171,9 +174,31 @@ class _B0Features(nn.Module):
 
 
 def _v2s_weights():
-    """The reference asks for ``EfficientNet_V2_S_Weights.IMAGENET1K_V1`` (sfe.py:111), a download.  Use them
-    only when explicitly requested (``EWVIT_PRETRAINED=1``, needs the file in the torch hub cache)."""
-    if os.environ.get("EWVIT_PRETRAINED", "0") == "1":
-        from torchvision.models import EfficientNet_V2_S_Weights
-        return EfficientNet_V2_S_Weights.IMAGENET1K_V1
-    return None
+    """The reference builds ``efficientnet_v2_s(weights=EfficientNet_V2_S_Weights.IMAGENET1K_V1)`` (sfe.py:111-112) and
+    freezes its first six tensors.  Same here whenever the checkpoint is in the torch hub cache or can be downloaded;
+    when it cannot (no network), warn loudly -- the backbone is then RANDOMLY initialised with a frozen random stem,
+    which is fine for loading a trained checkpoint or for benchmarks but not for training from scratch.
+    ``EWVIT_ALLOW_RANDOM_BACKBONE=1`` (tests, benchmarks) skips the attempt and the warning."""
+    if os.environ.get("EWVIT_ALLOW_RANDOM_BACKBONE", "0") == "1":
+        return None
+    from torchvision.models import EfficientNet_V2_S_Weights
+    weights = EfficientNet_V2_S_Weights.IMAGENET1K_V1
+    import socket
+    old = socket.getdefaulttimeout()
+    try:
+        socket.setdefaulttimeout(10)
+        weights.get_state_dict(progress=False, check_hash=False)       # hub cache hit, or download
+        return weights
+    except Exception as e:                                             # noqa: BLE001 (URLError, OSError, hash errors ...)
+        _warn_random_backbone("EfficientNetV2-S (torchvision IMAGENET1K_V1)", e)
+        return None
+    finally:
+        socket.setdefaulttimeout(old)
+
+
+def _warn_random_backbone(what, err):
+    import warnings
+    warnings.warn(f"{what} ImageNet weights could not be loaded ({type(err).__name__}: {err}); the reference starts from "
+                  "them (network/sfe.py:109-112).  This backbone is RANDOMLY initialised and its first six tensors are "
+                  "frozen as in the reference: load a trained checkpoint before use, or put the weights in the torch hub "
+                  "cache.  Set EWVIT_ALLOW_RANDOM_BACKBONE=1 to silence this.", stacklevel=3)

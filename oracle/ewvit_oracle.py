@@ -98,14 +98,14 @@ _BACKBONE_CACHE: dict = {}
 def backbone_v2s_features(sd: SD, p: str, x):
     """torchvision efficientnet_v2_s(...).features, network/sfe.py:111-113,150. p = "<...>.efficient_net."."""
     from torchvision.models import efficientnet_v2_s
-    key = id(sd), p
+    key = id(sd), p, str(x.device)
     net = _BACKBONE_CACHE.get(key)
     if net is None:
         net = efficientnet_v2_s(weights=None)
         net.classifier = torch.nn.Identity()
         sub = {k[len(p):]: v for k, v in sd.items() if k.startswith(p)}
         net.load_state_dict(sub, strict=True)
-        net.eval()
+        net.eval().to(x.device)
         _BACKBONE_CACHE.clear()
         _BACKBONE_CACHE[key] = net
     with torch.no_grad():
@@ -173,6 +173,13 @@ def sfe_forward(sd: SD, p: str, x, cfg=DEFAULT_CONFIG, output_mode="feature_map"
     return sfe_head(sd, p, backbone_v2s_features(sd, p + "efficient_net.", x), cfg, output_mode)
 
 
+def sfe_b0_forward(sd: SD, p: str, x, cfg=DEFAULT_CONFIG, output_mode="feature_map"):
+    """network/sfe.py:145-173 with the EfficientNet-b0 backbone (selected_efficient_net=0, sfe.py:109,148):
+    the standalone ``sfe`` (feature map) and ``sfe_cls`` (``output_mode='cls'``) branches of model.py:38-51."""
+    from .effnet_b0 import extract_features
+    return sfe_head(sd, p, extract_features(sd, p + "efficient_net.", x), cfg, output_mode)
+
+
 # --------------------------------------------------------------------------- DAMA
 def cross_attention(sd: SD, p: str, xn, ctx, heads: int):
     """network/dama.py:33-53 with kv_include_self=True: keys/values = cat(xn, ctx)."""
@@ -226,7 +233,7 @@ def dama_forward(sd: SD, p: str, x, batch_size=16, cfg=DEFAULT_CONFIG):
     """network/dama.py:171-206: serial chunk loop over K, per-video mean."""
     b, k = x.shape[:2]
     dim = sd[p + "gate_net.2.weight"].shape[1] // 2
-    acc = {n: torch.zeros(b, dim) for n in ("fused", "space", "freq")}
+    acc = {n: torch.zeros(b, dim, device=x.device) for n in ("fused", "space", "freq")}
     for s in range(0, k, batch_size):
         e = min(s + batch_size, k)
         out = dama_process_frame(sd, p, x[:, s:e].flatten(0, 1), cfg)
@@ -243,11 +250,29 @@ def classifier(sd: SD, feats):
 
 
 def detector_forward(sd: SD, x, batch_size: int, ablation: str = "dynamic", cfg=DEFAULT_CONFIG):
-    """network/model.py:70-161, eval mode.  ``dynamic`` only needs ``dama.*`` and
-    ``classifier.*`` keys; the two b0 ablation branches need ``sfe*.`` keys and the
-    EfficientNet-b0 restatement (``oracle/effnet_b0.py``)."""
+    """network/model.py:70-161, eval mode.  ``dynamic`` only needs ``dama.*`` and ``classifier.*`` keys;
+    ``sfe_only`` needs ``sfe_cls.*``; ``sfe_mwt`` needs ``sfe.*``, ``mwt.*``, ``fusion_gate.*``, ``classifier.*``
+    (b0 backbone: ``oracle/effnet_b0.py``)."""
     with torch.no_grad():
         if ablation == "dynamic":
             d = dama_forward(sd, "dama.", x, batch_size, cfg)
             return {"logits": classifier(sd, d["fused"]), **d}
-        raise NotImplementedError(f"oracle: ablation {ablation!r} not restated yet")
+        b, k = x.shape[:2]
+        chunks = [x[:, s:min(s + batch_size, k)].flatten(0, 1) for s in range(0, k, batch_size)]   # model.py:103-105,125-127
+        if ablation == "sfe_only":                 # model.py:100-118
+            per_frame = torch.cat([sfe_b0_forward(sd, "sfe_cls.", c, cfg, "cls").view(b, -1, 1) for c in chunks], dim=1)
+            return {"logits": per_frame.mean(dim=1), "model": "sfe_only"}
+        if ablation == "sfe_mwt":                  # model.py:119-161
+            dim = sd["classifier.0.weight"].shape[1]
+            sfe_parts, mwt_parts = [], []
+            for c in chunks:
+                s_ = F.adaptive_avg_pool2d(sfe_b0_forward(sd, "sfe.", c, cfg), 1).flatten(1)         # :130-131
+                sfe_parts.append(s_.view(b, -1, dim))
+                mwt_parts.append(mwt_forward(sd, "mwt.", c).flatten(1).view(b, -1, dim))             # :136-138
+            sfe_mean = torch.cat(sfe_parts, dim=1).mean(dim=1)                                       # :142-143
+            mwt_mean = torch.cat(mwt_parts, dim=1).mean(dim=1)
+            comb = torch.cat([sfe_mean, mwt_mean], dim=1)
+            gate = F.relu(comb @ sd["fusion_gate.0.weight"].t() + sd["fusion_gate.0.bias"]).softmax(dim=1)   # :146-148 (ReLU, eval dropout)
+            fused = sfe_mean * gate[:, 0:1] + mwt_mean * gate[:, 1:2]                                # :150-152
+            return {"logits": classifier(sd, fused), "sfe": sfe_mean, "mwt": mwt_mean, "model": "sfe_mwt"}
+        raise ValueError(f"Invalid ablation config: {ablation}.")

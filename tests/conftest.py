@@ -3,6 +3,8 @@ import sys
 
 import pytest
 
+os.environ.setdefault("EWVIT_ALLOW_RANDOM_BACKBONE", "1")     # tests use key-addressed weights, never ImageNet ones
+
 TESTS = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(TESTS)
 PKG = os.path.join(REPO, "efficient-wavelet-vit_b200")
@@ -13,6 +15,8 @@ for p in (PKG, REPO, TESTS):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # an eval-mode call that silently drops to the PyTorch composition (grad mode left on) must fail a test, not pass slowly
+    config.addinivalue_line("filterwarnings", "error:.*builds a graph through the PyTorch composition")
 
 
 @pytest.fixture(scope="session")

@@ -149,6 +149,20 @@ with torch.no_grad():
     gold["detector_config1"] = {"seed": 42, "shape": [1, 8, 3, 224, 224], "batch_size": 8,
                                 **{k: small(v) for k, v in out1.items()}}
 
+    # ---- a-10: the two b0 ablation branches (model.py:100-161), ragged last chunk (K=5, batch_size=2) and K=4/bs=4 ----
+    for tag, vv, bs in (("k5", vids, 2), ("k4", seeded_randn((2, 4, 3, 224, 224), 33), 4)):
+        for mode in ("sfe_only", "sfe_mwt"):
+            o = model(vv, batch_size=bs, ablation=mode)
+            gold[f"detector_{mode}_{tag}"] = {"seed": 31 if tag == "k5" else 33, "shape": list(vv.shape), "batch_size": bs,
+                                              **{k: (small(v) if torch.is_tensor(v) else v) for k, v in o.items()}}
+            print(mode, tag, "logits:", o["logits"].flatten().tolist())
+    # b0 backbone (third-party stand-in, see oracle/effnet_b0.py) and the b0-fed EfficientViT in both output modes
+    b0 = model.sfe.efficient_net.extract_features(frames)
+    gold["b0_feat_mean"] = small(b0.mean(dim=(2, 3)))
+    gold["b0_feat_crop"] = small(b0[:, :16])
+    gold["sfe_b0_out"] = small(model.sfe(frames))
+    gold["sfe_cls_out"] = small(model.sfe_cls(frames))
+
     # ---- quirk (ii): more than 64 frames per chunk raises (sfe.py:158-159) ----
     try:
         model.dama.sfe(torch.zeros(65, 3, 224, 224))

@@ -100,12 +100,11 @@ def test_fold_bn_and_tap_major_layout():
     assert float(w[..., 5:].abs().max()) == 0.0
 
 
-def test_train_mode_torch_composition_matches_oracle_in_eval_math(model, manifest, monkeypatch):
+def test_train_mode_torch_composition_matches_oracle_in_eval_math(model, manifest):
     """The PyTorch composition kept for training is the same math as the oracle: check the DAMA fusion tail and
-    the ViT head on CPU (sub-modules with no Haar kernel on their path), in eval mode via EWVIT_FORCE_TORCH."""
+    the ViT head on CPU (plain sub-modules with no native kernel on their path), in eval mode."""
     from _weights import fill_module_, seeded_randn
     from oracle import ewvit_oracle as O
-    monkeypatch.setenv("EWVIT_FORCE_TORCH", "1")
     fill_module_(model, seed=0)
     model.eval()
     sd = {k: v for k, v in model.state_dict().items()}
@@ -168,3 +167,60 @@ def test_mwt_head_block_diagonal_packing(model):
         for (oc, ic, dy, dx) in ((0, 0, 0, 0), (17, 2, 2, 2), (9, 1, 1, 0)):
             assert float(wbd[18 * g + oc, dy, dx, 3 * g + ic]) == float(wg[oc, ic, dy, dx].bfloat16())
     assert float(wbd[54:].abs().max()) == 0.0 and float(wbd[:, :, 3].abs().max()) == 0.0
+
+
+def test_native_runner_cache_invalidation_rules(model):
+    """The runner cache key lists (key, data_ptr, version, device) per tensor; train()/eval() transitions and
+    load_state_dict drop it; `.data` writes are the documented blind spot that `invalidate_native_cache()` covers."""
+    mwt = model.dama.mwt
+    builds = []
+    build = lambda: builds.append(1) or len(builds)
+    mwt.eval()
+    assert mwt._native_runner(build) == 1 and mwt._native_runner(build) == 1          # cached
+    with torch.no_grad():
+        mwt.freq_conv[0].weight.mul_(1.0)                                              # in-place write: version bump
+    assert mwt._native_runner(build) == 2
+    w = mwt.freq_conv[0].weight
+    w.data = w.data.clone()                                                            # storage swap: data_ptr changes
+    assert mwt._native_runner(build) == 3
+    w.data.mul_(1.0)                                                                   # invisible: neither version nor pointer move
+    assert mwt._native_runner(build) == 3
+    mwt.invalidate_native_cache()
+    assert mwt._native_runner(build) == 4
+    w.data.mul_(1.0)
+    model.train()
+    model.eval()                                                                       # every train -> eval transition rebuilds
+    assert mwt._native_runner(build) == 5
+    mwt.load_state_dict(mwt.state_dict())
+    assert mwt._native_runner(build) == 6
+    # two tensors swapping places cannot cancel out (the old key was a SUM over tensors)
+    sig = mwt._native_signature()
+    assert isinstance(sig, tuple) and len(sig) == len(mwt.state_dict())
+    model.train()
+
+
+def test_eval_with_grad_enabled_takes_the_autograd_composition(model):
+    """Eval mode + grad mode on + trainable parameters: the native outputs would carry no grad_fn, so the call is routed to
+    the PyTorch composition (with a warning); under torch.no_grad() the native path is chosen (raises here: CPU tensor)."""
+    import warnings
+    from network import _native
+    model.eval()
+    cuda_like = torch.zeros(1, 3, 8, 8)
+
+    class FakeCuda:                       # _use_native only inspects .is_cuda / .requires_grad
+        is_cuda, requires_grad = True, False
+
+    _native._WARNED.clear()
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        assert model.dama.mwt._use_native(FakeCuda()) is False
+    assert any("torch.no_grad()" in str(w.message) for w in rec)
+    with torch.no_grad():
+        assert model.dama.mwt._use_native(FakeCuda()) is True
+    for p in model.dama.mwt.parameters():
+        p.requires_grad_(False)
+    assert model.dama.mwt._use_native(FakeCuda()) is True      # frozen module: nothing needs a graph
+    for p in model.dama.mwt.parameters():
+        p.requires_grad_(True)
+    del cuda_like
+    model.train()

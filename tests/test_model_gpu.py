@@ -2,8 +2,8 @@
 key-addressed weights (rows a-3 .. a-10), plus the committed golden outputs of the unmodified reference.
 
 Floating point, bf16 tensor-core operands with fp32 accumulation: the stated tolerance is
-``|got - ref| <= TOL * max|ref|`` per tensor with TOL = 3e-2 for everything downstream of a bf16 GEMM/conv chain
-(measured errors are printed; they sit around 3e-3..1e-2), 1e-4 for the fp32-only DAMA tail, and identical
+``|got - ref| <= TOL * max|ref|`` per tensor with TOL = 1.5e-2 for everything downstream of a bf16 GEMM/conv chain
+(measured errors are printed; they sit around 2e-3..7e-3), 1e-4 for the fp32-only DAMA tail, and identical
 real/fake decisions (sign of the logit) wherever |logit_ref| exceeds the tolerance."""
 import pytest
 import torch
@@ -13,7 +13,7 @@ from oracle import ewvit_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-TOL = 3e-2
+TOL = 1.5e-2
 
 
 def rel_err(got, ref):
@@ -241,16 +241,56 @@ def test_load_state_dict_invalidates_native_cache(detector, dama_sd, frames):
     assert not torch.equal(a, b) and torch.equal(a, c)
 
 
-def test_ablation_modes_run_native_heads(detector):
-    """sfe_only / sfe_mwt keep the reference's dict keys and shapes (b0 branches; parity of the b0 backbone is a
-    'next' row -- here: finite outputs, right shapes, native kernels for MWT and the ViT head)."""
-    x = seeded_randn((2, 3, 3, 224, 224), 93).cuda()
+@pytest.fixture(scope="module")
+def ablation_sd(manifest):
+    from _weights import state_dict_from_manifest
+    return state_dict_from_manifest(manifest, seed=0, prefixes=("sfe.", "sfe_cls.", "mwt.", "fusion_gate.", "classifier."))
+
+
+@pytest.mark.parametrize("tag", ["k5", "k4"])
+@pytest.mark.parametrize("mode", ["sfe_only", "sfe_mwt"])
+def test_detector_ablation_modes_match_reference_golden(detector, ablation_sd, golden, mode, tag):
+    """`model(x, batch_size, 'sfe_only' | 'sfe_mwt')` (model.py:100-161; b0 branches): same dict keys, values within the
+    bf16 tolerance of the outputs of the unmodified reference (golden) and of the oracle, identical decisions."""
+    g = golden[f"detector_{mode}_{tag}"]
+    x = seeded_randn(tuple(g["shape"]), g["seed"])
     with torch.no_grad():
-        a = detector(x, 2, "sfe_only")
-        b = detector(x, 2, "sfe_mwt")
-    assert a["model"] == "sfe_only" and a["logits"].shape == (2, 1) and torch.isfinite(a["logits"]).all()
-    assert b["model"] == "sfe_mwt" and b["logits"].shape == (2, 1) and b["sfe"].shape == (2, 128) and b["mwt"].shape == (2, 128)
-    assert torch.isfinite(b["logits"]).all()
+        out = detector(x.cuda(), g["batch_size"], mode)
+    ref = O.detector_forward(ablation_sd, x, g["batch_size"], mode)
+    assert out["model"] == mode and sorted(out) == sorted(k for k in g if k not in ("seed", "shape", "batch_size"))
+    assert detector.ablation == mode
+    for k in (("logits",) if mode == "sfe_only" else ("sfe", "mwt", "logits")):
+        check(f"{mode}/{tag}[{k}] vs oracle", out[k], ref[k])
+        check(f"{mode}/{tag}[{k}] vs reference golden", out[k], g[k])
+    tol = TOL * float(g["logits"].abs().max())
+    decided = g["logits"].abs() > tol
+    assert torch.equal((out["logits"].cpu() >= 0)[decided], (g["logits"] >= 0)[decided])
+
+
+def test_sfe_b0_module_both_output_modes(detector, ablation_sd, frames, golden):
+    """Standalone `EfficientViT` on the EfficientNet-b0 backbone (sfe.py:109,148), feature-map and cls modes."""
+    with torch.no_grad():
+        y = detector.sfe(frames.cuda())
+        c = detector.sfe_cls(frames.cuda())
+    assert y.shape == (2, 128, 1, 1) and c.shape == (2, 1)
+    check("sfe (b0, feature_map) vs reference golden", y, golden["sfe_b0_out"])
+    check("sfe_cls (b0, cls) vs reference golden", c, golden["sfe_cls_out"])
+
+
+def test_full_shape_config4_eval_scoring_call(detector, dama_sd):
+    """BASELINE configs[3] shape of ONE eval call (eval.py:135-194): 8 videos x 300 frames, batch_size 8 -> the reference runs
+    37 chunks of 64 frames + a ragged chunk of 32; here 2400 frames go through the 512-frame macro-batch splitter (4 x 512 +
+    352, macro-batch boundaries fall inside videos and inside chunks).  Per-video logits / features vs the fp32 CPU oracle."""
+    x = seeded_randn((8, 300, 3, 224, 224), 101)
+    with torch.no_grad():
+        out = detector(x.cuda(), 8, "dynamic")
+        torch.cuda.synchronize()
+    ref = O.detector_forward(dama_sd, x, 8, "dynamic")
+    for k in ("fused", "space", "freq", "logits"):
+        check(f"8x300 frames [{k}]", out[k], ref[k])
+    tol = TOL * float(ref["logits"].abs().max())
+    decided = ref["logits"].abs() > tol
+    assert torch.equal((out["logits"].cpu() >= 0)[decided], (ref["logits"] >= 0)[decided])
 
 
 def test_forward_uint8_equals_forward_on_normalised_frames(detector):

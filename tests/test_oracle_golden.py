@@ -90,3 +90,51 @@ def test_more_than_64_frames_per_chunk_raises(golden, dama_sd):
     assert golden["n65_raises"]
     with pytest.raises(RuntimeError):
         O.vit_tokens_from_features(dama_sd, "dama.sfe.", torch.zeros(65, 1280, 7, 7))
+
+
+# ---------------------------------------------------------------- ablation branches (model.py:100-161)
+@pytest.fixture(scope="module")
+def ablation_sd(manifest):
+    from _weights import state_dict_from_manifest
+    return state_dict_from_manifest(manifest, seed=0, prefixes=("sfe.", "sfe_cls.", "mwt.", "fusion_gate.", "classifier."))
+
+
+def test_b0_backbone_restatement(golden, ablation_sd, frames):
+    """oracle/effnet_b0.py (functional) vs the b0 module the reference ran on (two implementations of the
+    published efficientnet_pytorch algorithm; upstream itself is absent: PARITY UNPINNED at that boundary)."""
+    from oracle.effnet_b0 import extract_features, same_pad
+    assert same_pad(224, 3, 2) == (0, 1) and same_pad(112, 3, 1) == (1, 1) and same_pad(56, 5, 2) == (1, 2)
+    assert same_pad(14, 5, 1) == (2, 2) and same_pad(14, 5, 2) == (1, 2) and same_pad(7, 3, 1) == (1, 1)
+    feat = extract_features(ablation_sd, "sfe.efficient_net.", frames)
+    assert feat.shape == (2, 1280, 7, 7)
+    assert torch.allclose(feat.mean(dim=(2, 3)), golden["b0_feat_mean"], **TOL)
+    assert torch.allclose(feat[:, :16], golden["b0_feat_crop"], **TOL)
+
+
+def test_sfe_b0_both_output_modes(golden, ablation_sd, frames):
+    with torch.no_grad():
+        y = O.sfe_b0_forward(ablation_sd, "sfe.", frames)
+        c = O.sfe_b0_forward(ablation_sd, "sfe_cls.", frames, output_mode="cls")
+    assert y.shape == (2, 128, 1, 1) and c.shape == (2, 1)
+    assert torch.allclose(y, golden["sfe_b0_out"], **TOL)
+    assert torch.allclose(c, golden["sfe_cls_out"], **TOL)
+
+
+@pytest.mark.parametrize("mode", ["sfe_only", "sfe_mwt"])
+@pytest.mark.parametrize("tag", ["k5", "k4"])
+def test_detector_ablation_modes(golden, ablation_sd, mode, tag):
+    g = golden[f"detector_{mode}_{tag}"]
+    x = seeded_randn(tuple(g["shape"]), g["seed"])
+    out = O.detector_forward(ablation_sd, x, g["batch_size"], mode)
+    assert out["model"] == g["model"] == mode
+    keys = ("logits",) if mode == "sfe_only" else ("logits", "sfe", "mwt")
+    assert set(out) == set(k for k in g if k not in ("seed", "shape", "batch_size"))
+    for k in keys:
+        assert out[k].shape == g[k].shape
+        assert torch.allclose(out[k], g[k], **TOL), k
+    assert torch.equal(out["logits"] >= 0, g["logits"] >= 0)
+
+
+def test_invalid_ablation_raises(ablation_sd):
+    with pytest.raises(ValueError):
+        O.detector_forward(ablation_sd, torch.zeros(1, 1, 3, 224, 224), 1, "nope")
