@@ -448,7 +448,7 @@ constexpr int kSeMaxC = 12 * 128;          // FC1 keeps one weight row (c / 128 
 __global__ void __launch_bounds__(kSeThreads) se_gate_kernel(const float *__restrict__ pooled, const float *__restrict__ w1,
                                                              const float *__restrict__ b1, const float *__restrict__ w2t,
                                                              const float *__restrict__ b2, float *__restrict__ gate, int n, int c, int sq,
-                                                             int out_bf16) {
+                                                             int out_bf16, int parts) {
     extern __shared__ __align__(16) float se_sm[];
     float *s_pool = se_sm;                 // [kSeF][c]
     float *s_hid = se_sm + kSeF * c;       // [kSeF][sq]
@@ -458,8 +458,15 @@ __global__ void __launch_bounds__(kSeThreads) se_gate_kernel(const float *__rest
     const int c4 = c >> 2;
     for (int i = tid; i < kSeF * c4; i += kSeThreads) {
         const int f = i / c4;
-        reinterpret_cast<float4 *>(s_pool)[i] =
-            f < nf ? __ldg(reinterpret_cast<const float4 *>(pooled + (long long)(f0 + f) * c) + (i - f * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f < nf) {                      // partial means of the depthwise kernel's (band, segment) units, fixed order
+            const float4 *pp = reinterpret_cast<const float4 *>(pooled + (long long)(f0 + f) * parts * c) + (i - f * c4);
+            for (int q = 0; q < parts; ++q) {
+                const float4 u = __ldg(pp + (long long)q * c4);
+                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+            }
+        }
+        reinterpret_cast<float4 *>(s_pool)[i] = v;
     }
     __syncthreads();
     for (int j = warp; j < sq; j += kSeThreads / 32) {
@@ -703,7 +710,7 @@ extern "C" int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const floa
         EWVIT_CUDA_OK(cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         if (dev >= 0 && dev < 64) se_attr[dev] = true;
     }
-    se_gate_kernel<<<(unsigned)((n + kSeF - 1) / kSeF), kSeThreads, gate_smem, (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, gate_ws, n, c, sq, 0);
+    se_gate_kernel<<<(unsigned)((n + kSeF - 1) / kSeF), kSeThreads, gate_smem, (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, gate_ws, n, c, sq, 0, 1);
     EWVIT_LAUNCH_OK();
     const long long total8 = (long long)n * hw * (c / 8);
     long long blocks = (total8 + 255) / 256;
@@ -715,9 +722,9 @@ extern "C" int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const floa
 }
 
 // Squeeze-excitation gate only (the scaling is fused into ewvit_conv1x1_gated_nhwc_bf16).
-extern "C" int ewvit_se_gate_fwd(const float *pooled, const float *w1, const float *b1, const float *w2t, const float *b2, int n,
-                                 int c, int sq, void *gate, int gate_bf16, void *stream) {
-    EWVIT_REQUIRE(n >= 0 && c > 0 && sq > 0, EWVIT_ERR_INVALID_ARG, "ewvit_se_gate_fwd: bad sizes");
+extern "C" int ewvit_se_gate_fwd(const float *pooled, int pool_parts, const float *w1, const float *b1, const float *w2t, const float *b2,
+                                 int n, int c, int sq, void *gate, int gate_bf16, void *stream) {
+    EWVIT_REQUIRE(n >= 0 && c > 0 && sq > 0 && pool_parts >= 1, EWVIT_ERR_INVALID_ARG, "ewvit_se_gate_fwd: bad sizes");
     if (n == 0) return EWVIT_OK;
     EWVIT_REQUIRE(pooled && w1 && b1 && w2t && b2 && gate && ewvit_aligned16(gate) && ewvit_aligned16(pooled) &&
                       ewvit_aligned16(w1) && ewvit_aligned16(w2t) && ewvit_aligned16(b2), EWVIT_ERR_INVALID_ARG,
@@ -733,7 +740,7 @@ extern "C" int ewvit_se_gate_fwd(const float *pooled, const float *w1, const flo
         EWVIT_CUDA_OK(cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         if (dev >= 0 && dev < 64) se_attr[dev] = true;
     }
-    se_gate_kernel<<<(unsigned)((n + kSeF - 1) / kSeF), kSeThreads, gate_smem, (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, static_cast<float *>(gate), n, c, sq, gate_bf16 ? 1 : 0);
+    se_gate_kernel<<<(unsigned)((n + kSeF - 1) / kSeF), kSeThreads, gate_smem, (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, static_cast<float *>(gate), n, c, sq, gate_bf16 ? 1 : 0, pool_parts);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }

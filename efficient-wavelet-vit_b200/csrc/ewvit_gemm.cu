@@ -35,6 +35,10 @@ constexpr int kMaxHalo = 8;                     // A_IM2COL: halo ring depth (TM
 constexpr int kFlat3Rows = BM + 8;               // 136 rows = 17 swizzle atoms: rows [m0 - 1, m0 + 135) cover the shifts 0..2
 constexpr int kFlat3ABytes = kFlat3Rows * BK * 2; // 17408
 constexpr int kStgBytes = 32 * 64;               // one epilogue chunk: 32 rows x 32 bf16, dense, 64B-swizzled (TMA store box)
+constexpr int kGateFrames = 4;                   // A_SCALED: SE gates of the (<= 4) frames an M tile touches, staged in shared memory
+constexpr int kGateMaxK = 1536;
+constexpr int kGateBytes = kGateFrames * kGateMaxK * 2;
+constexpr int kGateChunks = kGateBytes / 16 / (32 * kBuilderWarps);   // 16-byte chunks per builder thread
 // Epilogue warps come in groups of four (one warp per TMEM lane quarter).  Kernels without builder warps run FOUR
 // groups: two per accumulator stage, each draining half of the tile's columns -- short-K layers are bound by the
 // epilogue's latency chain (tcgen05.ld -> MUFU -> staging -> TMA store, ~1200 cycles per 32x32 chunk with two warps per
@@ -49,8 +53,9 @@ struct Cfg {
     static constexpr int kHalves = kEpiGroups / 2;                       // column halves per accumulator stage
     static constexpr int kThreads = 64 + 32 * kEpiWarps + (kBuilder ? 32 * kBuilderWarps : 0);
     static constexpr int kStagingBytes = kEpiWarps * kStgBytes;          // per-warp staging buffers of the epilogue
-    static constexpr int kOperandBytes = (kWideEpi ? 160 : 200) * 1024;  // operand stages (+ halo buffers)
-    static constexpr int kPayloadBytes = kOperandBytes + kStagingBytes;  // barriers live right behind
+    static constexpr int kOperandBytes = (kWideEpi ? 160 : kBuilder ? 192 : 200) * 1024;  // operand stages (+ halo buffers)
+    static constexpr int kGateOff = kOperandBytes + kStagingBytes;       // builder kernels: staged SE gates
+    static constexpr int kPayloadBytes = kGateOff + (kBuilder ? kGateBytes : 0);  // barriers live right behind
     static constexpr int kSmemBytes = kPayloadBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
@@ -97,6 +102,7 @@ struct GemmParams {
     int a_gate_bf16;
     int a_hw;              // rows (pixels) per frame
     int a_k;               // K = row pitch of A and of the gate
+    int a_gate_smem;       // the gates of a tile's frames are staged in shared memory once per tile (bf16 gates, <= kGateFrames frames per tile)
     int flat3;           // A_FLAT 3x3 conv, "row-shared" taps: one ring slot = (dy, channel chunk) holds ONE window of
                          // kFlat3Rows activation rows and the three weight tiles of dx = 0,1,2; the three A operands are the
                          // same window read at a start address shifted by 0/1/2 rows, so every activation row crosses
@@ -407,6 +413,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t chunk_off = (uint32_t)rb * 128u + (((uint32_t)j ^ (uint32_t)rb) << 4);
             const int last_frame = (int)((p.M - 1) / p.a_hw);
             uint32_t g = 0;
+            // Gates in shared memory (bf16 gates, the engine's case).  Fetching them from global memory per k-block was the
+            // stall of this kernel (ncu: issue-active 19 %, 16 dependent L2 round trips per builder thread and k-block): now
+            // the [frames of the tile][K] gate block is staged once per tile -- its 16-byte chunks are requested one tile
+            // AHEAD into registers, so the copy costs two named barriers and no exposed latency.
+            const bool gsm = p.a_gate_smem != 0;
+            const uint32_t gate_sm = smem_base + (uint32_t)Cfg<kEpi, kBuilder>::kGateOff;
+            const int kchunks = p.a_k >> 3;                       // 16-byte chunks per gate row
+            uint4 gpre[kGateChunks];
+            auto gate_prefetch = [&](int w2) {
+                const int f0n = (int)(((long long)(w2 % p.tiles_m) * BM) / p.a_hw);
+#pragma unroll
+                for (int q = 0; q < kGateChunks; ++q) {
+                    const int ch = btid + q * (32 * kBuilderWarps);
+                    const int fr = ch / kchunks, cc = ch - fr * kchunks;
+                    gpre[q] = make_uint4(0u, 0u, 0u, 0u);
+                    if (fr < kGateFrames && w2 < total_work)
+                        gpre[q] = __ldg(reinterpret_cast<const uint4 *>(static_cast<const __nv_bfloat16 *>(p.a_gate) +
+                                                                        (long long)min(f0n + fr, last_frame) * p.a_k) + cc);
+                }
+            };
+            if (gsm) gate_prefetch(blockIdx.x);
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const int m_t = w % p.tiles_m;
                 const int sp = (w / p.tiles_m) / p.tiles_n;
@@ -416,14 +443,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int goff[16];
                 {
                     const long long row0 = (long long)m_t * BM + rb;
+                    const int f0 = (int)(((long long)m_t * BM) / p.a_hw);
                     int fr = (int)(row0 / p.a_hw);
                     int rem = (int)(row0 - (long long)fr * p.a_hw);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        goff[i] = min(fr, last_frame) * p.a_k + j * 8;
+                        goff[i] = gsm ? (min(fr, last_frame) - f0) * p.a_k * 2 + j * 16      // byte offset inside the staged block
+                                      : min(fr, last_frame) * p.a_k + j * 8;
                         rem += 8;
                         while (rem >= p.a_hw) { rem -= p.a_hw; ++fr; }
                     }
+                }
+                if (gsm) {
+                    asm volatile("bar.sync 3, %0;" ::"n"(32 * kBuilderWarps) : "memory");   // every builder is done with the previous tile's gates
+#pragma unroll
+                    for (int q = 0; q < kGateChunks; ++q) {
+                        const int ch = btid + q * (32 * kBuilderWarps);
+                        if (ch < kGateFrames * kchunks)
+                            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(gate_sm + (uint32_t)ch * 16u), "r"(gpre[q].x), "r"(gpre[q].y),
+                                         "r"(gpre[q].z), "r"(gpre[q].w) : "memory");
+                    }
+                    asm volatile("bar.sync 3, %0;" ::"n"(32 * kBuilderWarps) : "memory");
+                    gate_prefetch(w + gridDim.x);
                 }
                 for (int kb = kb0; kb < kb1; ++kb, ++g) {
                     const int stage = (int)(g % (uint32_t)nstages);
@@ -431,6 +472,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t phase = (g / (uint32_t)nstages) & 1u;
                     const bool kin = kb * BK + j * 8 < p.a_k;               // K tail: the tile holds zeros there
                     const uint32_t a_base = smem_base + stage * kStageB + chunk_off;
+                    if (gsm) {
+                        ewvit::mbar_wait(ewvit::smem_u32(&hfull[stage]), phase);
+                        const uint32_t gk = gate_sm + (uint32_t)kb * (BK * 2);
+#pragma unroll
+                        for (int b4 = 0; b4 < 2; ++b4) {
+                            uint4 gq[8], v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                gq[i] = make_uint4(0u, 0u, 0u, 0u);
+                                if (kin)
+                                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(gq[i].x), "=r"(gq[i].y), "=r"(gq[i].z), "=r"(gq[i].w)
+                                                 : "r"(gk + (uint32_t)goff[b4 * 8 + i]) : "memory");
+                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
+                                             : "r"(a_base + (b4 * 8 + i) * 1024) : "memory");
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const __nv_bfloat162 *vp = reinterpret_cast<const __nv_bfloat162 *>(&v[i]);
+                                const __nv_bfloat162 *gp2 = reinterpret_cast<const __nv_bfloat162 *>(&gq[i]);
+                                const __nv_bfloat162 o0 = __hmul2(vp[0], gp2[0]), o1 = __hmul2(vp[1], gp2[1]);
+                                const __nv_bfloat162 o2 = __hmul2(vp[2], gp2[2]), o3 = __hmul2(vp[3], gp2[3]);
+                                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + (b4 * 8 + i) * 1024),
+                                             "r"(*reinterpret_cast<const uint32_t *>(&o0)), "r"(*reinterpret_cast<const uint32_t *>(&o1)),
+                                             "r"(*reinterpret_cast<const uint32_t *>(&o2)), "r"(*reinterpret_cast<const uint32_t *>(&o3))
+                                             : "memory");
+                            }
+                        }
+                    } else
                     if (p.a_gate_bf16) {
                         // bf16 gates: one 16-byte load and four packed multiplies per 8-channel chunk (the product of two bf16
                         // values is exact in fp32, so HMUL2.BF16 rounds exactly like the fp32 path)
@@ -1507,6 +1576,8 @@ extern "C" int ewvit_conv1x1_gated_nhwc_bf16(const void *x, const void *gate, in
     p.a_gate_bf16 = gate_bf16 ? 1 : 0;
     p.a_hw = hw;
     p.a_k = cin;
+    // a 128-row tile touches at most (127 + hw - 1) / hw + 1 frames
+    p.a_gate_smem = (gate_bf16 && cin <= kGateMaxK && (BM - 1 + hw - 1) / hw + 1 <= kGateFrames) ? 1 : 0;
     p.N = cout;
     p.M = rows;
     p.tiles_m = (int)((rows + BM - 1) / BM);

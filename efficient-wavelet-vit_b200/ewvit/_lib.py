@@ -47,7 +47,9 @@ SIGNATURES = {
     "ewvit_conv_nhwc_bf16_ex": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, c_int, c_int, P]),
     "ewvit_dwconv3x3_nhwc_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "ewvit_se_apply_nhwc_bf16": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
-    "ewvit_se_gate_fwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, c_int, P]),
+    "ewvit_se_gate_fwd": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, P, c_int, P]),
+    "ewvit_dwconv_nhwc_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "ewvit_dwconv_pool_parts": (c_int, [c_int, c_int, c_int, c_int]),
     "ewvit_conv1x1_gated_nhwc_bf16": (c_int, [P, P, c_int, P, c_int, c_int, c_int, c_int, P, c_int, P, P, P]),
     "ewvit_mwt_head_mma_fwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "ewvit_mwt_upsample_fwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),

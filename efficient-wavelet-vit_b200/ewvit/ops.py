@@ -456,16 +456,51 @@ def se_apply(x, pooled, w1, b1, w2t, b2, gate_ws=None):
 
 
 def se_gate(pooled, w1, b1, w2t, b2, out=None, bf16=False):
-    """gate [n,c] = sigmoid(W2 silu(W1 pooled + b1) + b2), fp32 or (bf16=True) bf16."""
+    """gate [n,c] = sigmoid(W2 silu(W1 mean + b1) + b2), fp32 or (bf16=True) bf16; pooled is [n,c] means or [n,parts,c]
+    partial means (summed in index order)."""
     for t, nm in ((pooled, "pooled"), (w1, "w1"), (b1, "b1"), (w2t, "w2t"), (b2, "b2")):
         _check_f32(t, nm)
-    n, c = pooled.shape
+    n, c = pooled.shape[0], pooled.shape[-1]
+    parts = pooled.shape[1] if pooled.dim() == 3 else 1
     if out is None:
         out = torch.empty((n, c), dtype=torch.bfloat16 if bf16 else torch.float32, device=pooled.device)
     with torch.cuda.device(pooled.device):
-        check(load().ewvit_se_gate_fwd(pooled.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2t.data_ptr(), b2.data_ptr(), n, c,
+        check(load().ewvit_se_gate_fwd(pooled.data_ptr(), parts, w1.data_ptr(), b1.data_ptr(), w2t.data_ptr(), b2.data_ptr(), n, c,
                                        w1.shape[0], out.data_ptr(), int(out.dtype == torch.bfloat16), _stream()), "ewvit_se_gate_fwd")
     return out
+
+
+def dwconv_out_size(size, ksize, stride, same_tf=False):
+    """(output size, zero padding before) of one spatial axis: torchvision's symmetric pad k//2, or TensorFlow 'SAME'."""
+    if same_tf:
+        out = -(-size // stride)
+        total = max((out - 1) * stride + ksize - size, 0)
+        return out, total // 2
+    return (size + 2 * (ksize // 2) - ksize) // stride + 1, ksize // 2
+
+
+def dwconv(x, wkc, bias, ksize, stride, same_tf=False, act="silu", out=None, pooled=False):
+    """Depthwise k x k (3 | 5, stride 1 | 2) + bias + SiLU on NHWC bf16 x [n,h,w,c]; wkc [k*k, c] fp32 tap-major.
+    pooled=True also returns the SE squeeze as partial means [n, parts, c] fp32 (sum over parts = spatial mean)."""
+    _check_bf16(x, "x", 4)
+    _check_f32(wkc, "wkc")
+    n, h, wd, c = x.shape
+    if wkc.shape != (ksize * ksize, c):
+        raise EwvitError(f"dwconv: weights must be [{ksize * ksize}, {c}] (got {tuple(wkc.shape)})")
+    bias = _f32_or_none(bias, "bias", c)
+    ho, pt = dwconv_out_size(h, ksize, stride, same_tf)
+    wo, pl = dwconv_out_size(wd, ksize, stride, same_tf)
+    if out is None:
+        out = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=x.device)
+    pool = None
+    lib = load()
+    if pooled:
+        parts = lib.ewvit_dwconv_pool_parts(ho, wo, ksize, stride)
+        pool = torch.empty((n, parts, c), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.ewvit_dwconv_nhwc_bf16(x.data_ptr(), wkc.data_ptr(), bias.data_ptr(), n, h, wd, c, ksize, stride, pt, pl, ho, wo,
+                                         {None: 0, "silu": 4}[act], out.data_ptr(), _ptr(pool), _stream()), "ewvit_dwconv_nhwc_bf16")
+    return (out, pool) if pooled else out
 
 
 def conv1x1_gated(x, gate, w, bias=None, act=None, residual=None, out=None):

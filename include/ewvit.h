@@ -275,6 +275,17 @@ EWVIT_API int ewvit_stem_conv_u8_fwd(const uint8_t *x, const float *mean, const 
 EWVIT_API int ewvit_dwconv3x3_nhwc_bf16(const void *x, const float *w, const float *bias, int n, int h, int wd, int c,
                                         int stride, void *y, float *pooled, void *stream);
 
+/* Depthwise k x k (k = 3 | 5, stride 1 | 2) + bias + activation (act: 0 none, 4 SiLU) with explicit top/left zero padding and
+ * output size, so both torchvision's symmetric padding (EfficientNetV2-S: pad k/2, ho = (h-1)/s+1; network/sfe.py:111-113)
+ * and TensorFlow 'SAME' padding (efficientnet_pytorch b0: pad_top = total/2 with the odd pixel at the bottom/right,
+ * ho = ceil(h/s); network/sfe.py:109) are covered.  x [n,h,wd,c] bf16, w [k*k, c] fp32 (tap-major), bias [c], y [n,ho,wo,c]
+ * bf16; c even.  pooled (NULL to skip) receives the SE squeeze as ewvit_dwconv_pool_parts(ho, wo, k, s) partial means per
+ * frame: pooled[n, parts, c] fp32, whose sum over `parts` is the spatial mean of the stored result. */
+EWVIT_API int ewvit_dwconv_nhwc_bf16(const void *x, const float *w, const float *bias, int n, int h, int wd, int c, int ksize,
+                                     int stride, int pad_top, int pad_left, int ho, int wo, int act, void *y, float *pooled,
+                                     void *stream);
+EWVIT_API int ewvit_dwconv_pool_parts(int ho, int wo, int ksize, int stride);
+
 /* Squeeze-excitation (torchvision.ops.SqueezeExcitation with SiLU / Sigmoid): gate = sigmoid(W2 silu(W1 pooled + b1) + b2),
  * x *= gate in place.  x [n,hw,c] bf16, pooled [n,c] fp32, w1 [sq,c], b1 [sq], w2t [sq,c] (= fc2 weight transposed), b2 [c],
  * gate_ws [n,c] fp32 workspace (receives the gate). */
@@ -283,9 +294,10 @@ EWVIT_API int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const float
 
 /* Squeeze-excitation gate only: gate[n, c] = sigmoid(W2 silu(W1 pooled[n] + b1) + b2) (same operands as
  * ewvit_se_apply_nhwc_bf16); the scaling itself is then fused into ewvit_conv1x1_gated_nhwc_bf16.
- * gate_bf16 != 0: the gates are written as bf16 (what the gated conv multiplies fastest), else fp32. */
-EWVIT_API int ewvit_se_gate_fwd(const float *pooled, const float *w1, const float *b1, const float *w2t, const float *b2, int n,
-                                int c, int sq, void *gate, int gate_bf16, void *stream);
+ * pooled [n, pool_parts, c]: partial means as written by ewvit_dwconv_nhwc_bf16, summed here in index order (pool_parts = 1:
+ * plain [n, c] means).  gate_bf16 != 0: the gates are written as bf16 (what the gated conv multiplies fastest), else fp32. */
+EWVIT_API int ewvit_se_gate_fwd(const float *pooled, int pool_parts, const float *w1, const float *b1, const float *w2t, const float *b2,
+                                int n, int c, int sq, void *gate, int gate_bf16, void *stream);
 
 /* 1x1 convolution behind a squeeze-excitation block (MBConv project conv):
  *   y = act(((x * gate[frame]) W^T) + bias) + residual

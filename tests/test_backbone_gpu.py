@@ -173,6 +173,42 @@ def test_depthwise_and_squeeze(ops, c, stride, hw):
     _close(pooled, ref.mean(dim=(2, 3)), tol=5e-3, bf16_out=False)
 
 
+@pytest.mark.parametrize("c,k,stride,hw,same_tf", [
+    (256, 3, 2, (28, 28), False), (960, 3, 1, (14, 14), False), (1536, 3, 1, (7, 7), False), (960, 3, 2, (14, 14), False),
+    (64, 3, 1, (5, 9), False), (512, 3, 1, (14, 14), False), (768, 3, 1, (14, 14), False),
+    # EfficientNet-b0 shapes: TensorFlow 'SAME' padding, 5x5 kernels, channel counts that are not multiples of 64
+    (32, 3, 1, (112, 112), True), (96, 3, 2, (112, 112), True), (144, 5, 2, (56, 56), True), (240, 5, 1, (28, 28), True),
+    (240, 3, 2, (28, 28), True), (480, 5, 1, (14, 14), True), (672, 5, 2, (14, 14), True), (1152, 5, 1, (7, 7), True),
+    (1152, 3, 1, (7, 7), True), (40, 5, 2, (9, 11), True)])
+def test_depthwise_general(ops, c, k, stride, hw, same_tf):
+    """ewvit_dwconv_nhwc_bf16: k x k depthwise + bias + SiLU with torchvision (symmetric) or TF-SAME padding, plus the SE
+    squeeze as partial means -- vs fp32 torch on the same bf16 input (fp32 accumulation, tanh.approx SiLU: 1e-3)."""
+    n, (h, w) = 3, hw
+    x = seeded_randn((n, c, h, w), 11).bfloat16()
+    wt = seeded_randn((c, 1, k, k), 12) * (1.0 / k)
+    b = seeded_randn((c,), 13) * 0.1
+    if same_tf:
+        (ho, pt), (wo, pl) = ops.dwconv_out_size(h, k, stride, True), ops.dwconv_out_size(w, k, stride, True)
+        pb, pr = max((ho - 1) * stride + k - h, 0) - pt, max((wo - 1) * stride + k - w, 0) - pl
+        ref = F.silu(F.conv2d(F.pad(x.float(), (pl, pr, pt, pb)), wt, b, stride=stride, groups=c))
+    else:
+        ref = F.silu(F.conv2d(x.float(), wt, b, stride=stride, padding=k // 2, groups=c))
+    got, pooled = ops.dwconv(_nhwc(x).cuda(), wt.reshape(c, k * k).t().contiguous().cuda(), b.cuda(), k, stride, same_tf=same_tf,
+                             pooled=True)
+    assert got.shape == (n, ref.shape[2], ref.shape[3], c)
+    _close(got.permute(0, 3, 1, 2), ref, tol=1e-3)
+    assert pooled.shape[0] == n and pooled.shape[2] == c
+    _close(pooled.sum(dim=1), ref.mean(dim=(2, 3)), tol=5e-3, bf16_out=False)
+    # the gate kernel consumes the partial means directly
+    sq = 8
+    w1, b1 = seeded_randn((sq, c), 15) * c ** -0.5, seeded_randn((sq,), 16)
+    w2, b2 = seeded_randn((c, sq), 17) * sq ** -0.5, seeded_randn((c,), 18)
+    if c % 8 == 0:
+        gate = ops.se_gate(pooled, w1.cuda(), b1.cuda(), w2.t().contiguous().cuda(), b2.cuda())
+        gref = torch.sigmoid(F.silu(pooled.sum(dim=1).cpu() @ w1.t() + b1) @ w2.t() + b2)
+        _close(gate, gref, tol=1e-3, bf16_out=False)
+
+
 def test_se_apply(ops):
     n, c, sq, h, w = 4, 960, 40, 14, 14
     x = seeded_randn((n, c, h, w), 14).bfloat16()

@@ -46,6 +46,6 @@ for (c, co, hw) in ((960, 160, 14), (1536, 256, 7), (512, 128, 14)):
     w3 = (torch.randn(co, c, device="cuda") * 0.03).bfloat16()
     b3 = torch.zeros(co, device="cuda")
     r3 = torch.randn(512, hw, hw, co, device="cuda").bfloat16()
-    g3 = torch.rand(512, c, device="cuda")
+    g3 = torch.rand(512, c, device="cuda").bfloat16()
     run(f"conv1 {c}->{co} @{hw} project + residual", lambda: ops.conv_nhwc_bf16(x3, w3, 1, 1, bias=b3, act=None, residual=r3))
     run(f"conv1g {c}->{co} @{hw} gated project + residual", lambda: ops.conv1x1_gated(x3, g3, w3, bias=b3, act=None, residual=r3))
