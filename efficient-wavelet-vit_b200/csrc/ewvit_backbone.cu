@@ -20,7 +20,7 @@ template <typename TIn>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const TIn *__restrict__ x, const float *__restrict__ w,
                                                         const float *__restrict__ bias, __nv_bfloat16 *__restrict__ y,
                                                         int n, int h, int wd, int ho, int wo, int cout, int pad,
-                                                        const float *__restrict__ mean, const float *__restrict__ stdv) {
+                                                        const float *__restrict__ mean, const float *__restrict__ stdv, int in_pad) {
     // weights transposed to [27][cout] so that 4 consecutive output channels are one 16-byte shared-memory read;
     // pre-halved for the h*tanh(h)+h form of SiLU
     __shared__ __align__(16) float s_w[27 * kStemMaxC];
@@ -41,17 +41,18 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const TIn *__restrict__ 
         const int oy = (int)(t % ho);
         const long long img = t / ho;
         const int ox0 = qx * kStemPx;
-        // input patch: 3 channels x 3 rows x 9 columns (columns 2*ox0 - 1 .. 2*ox0 + 7)
+        // input patch: 3 channels x 3 rows x 9 columns (columns 2*ox0 - in_pad .. 2*ox0 - in_pad + 8); in_pad = 1: torchvision's
+        // symmetric padding, in_pad = 0: TensorFlow 'SAME' on an even size (the extra zero row/column sits at the bottom/right)
         float in[3][3][2 * kStemPx + 1];
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
-                const int iy = 2 * oy + dy - 1;
+                const int iy = 2 * oy + dy - in_pad;
                 const TIn *row = x + ((img * 3 + c) * h + (iy >= 0 && iy < h ? iy : 0)) * (long long)wd;
 #pragma unroll
                 for (int j = 0; j < 2 * kStemPx + 1; ++j) {
-                    const int ix = 2 * ox0 + j - 1;
+                    const int ix = 2 * ox0 + j - in_pad;
                     float v = 0.f;
                     if (iy >= 0 && iy < h && ix >= 0 && ix < wd) {
                         if (sizeof(TIn) == 1) v = s_lut[c * 256 + (int)__ldg(row + ix)];
@@ -568,14 +569,17 @@ __global__ void __launch_bounds__(256) se_scale_kernel(__nv_bfloat16 *__restrict
 }  // namespace
 
 static int stem_impl(const void *x, bool u8, const float *mean, const float *stdv, int n, int h, int wd, const float *w, const float *bias,
-                     int cout, void *y, int out_padded, void *stream) {
+                     int cout, void *y, int out_padded, void *stream, int same_tf = 0) {
     EWVIT_REQUIRE(n >= 0 && h > 0 && wd > 0, EWVIT_ERR_INVALID_ARG, "ewvit_stem_conv_fwd: bad sizes");
     if (n == 0) return EWVIT_OK;
     EWVIT_REQUIRE(x && w && bias && y && ewvit_aligned16(y), EWVIT_ERR_INVALID_ARG, "ewvit_stem_conv_fwd: NULL or misaligned pointer");
     EWVIT_REQUIRE(cout % 8 == 0 && cout <= kStemMaxC, EWVIT_ERR_UNSUPPORTED, "ewvit_stem_conv_fwd: cout must be a multiple of 8, <= 32");
     int rc = ewvit_check_device();
     if (rc != EWVIT_OK) return rc;
-    const int ho = (h - 1) / 2 + 1, wo = (wd - 1) / 2 + 1;
+    const int ho = (h - 1) / 2 + 1, wo = (wd - 1) / 2 + 1;          // = ceil(h / 2): the same for both padding rules
+    // TensorFlow 'SAME' (efficientnet_pytorch): total padding max((ho-1)*2 + 3 - h, 0), floor(total/2) of it on top/left
+    const int in_pad = same_tf ? (((ho - 1) * 2 + 3 - h) > 0 ? ((ho - 1) * 2 + 3 - h) / 2 : 0) : 1;
+    EWVIT_REQUIRE(!same_tf || h == wd, EWVIT_ERR_UNSUPPORTED, "ewvit_stem_conv_same_fwd: square frames only");
     const long long total = (long long)n * ho * ((wo + kStemPx - 1) / kStemPx);
     long long blocks = (total + 127) / 128;
     const long long cap = (long long)ewvit_num_sms() * 32;
@@ -583,11 +587,11 @@ static int stem_impl(const void *x, bool u8, const float *mean, const float *std
     if (u8)
         stem_conv_kernel<unsigned char><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char *>(x), w, bias,
                                                                                            static_cast<__nv_bfloat16 *>(y), n, h, wd, ho, wo, cout,
-                                                                                           out_padded ? 1 : 0, mean, stdv);
+                                                                                           out_padded ? 1 : 0, mean, stdv, in_pad);
     else
         stem_conv_kernel<float><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(static_cast<const float *>(x), w, bias,
                                                                                    static_cast<__nv_bfloat16 *>(y), n, h, wd, ho, wo, cout,
-                                                                                   out_padded ? 1 : 0, nullptr, nullptr);
+                                                                                   out_padded ? 1 : 0, nullptr, nullptr, in_pad);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }
@@ -595,6 +599,11 @@ static int stem_impl(const void *x, bool u8, const float *mean, const float *std
 extern "C" int ewvit_stem_conv_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
                                    void *y, void *stream) {
     return stem_impl(x, false, nullptr, nullptr, n, h, wd, w, bias, cout, y, 0, stream);
+}
+
+extern "C" int ewvit_stem_conv_same_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
+                                        void *y, void *stream) {
+    return stem_impl(x, false, nullptr, nullptr, n, h, wd, w, bias, cout, y, 0, stream, 1);
 }
 
 extern "C" int ewvit_stem_conv_padded_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,

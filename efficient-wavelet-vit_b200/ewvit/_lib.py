@@ -44,6 +44,7 @@ SIGNATURES = {
     "ewvit_stem_conv_u8_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P, c_int, P, c_int, P]),
     "ewvit_stem_conv_fwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P]),
     "ewvit_stem_conv_padded_fwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P]),
+    "ewvit_stem_conv_same_fwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P]),
     "ewvit_conv_nhwc_bf16_ex": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, c_int, c_int, P]),
     "ewvit_dwconv3x3_nhwc_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "ewvit_se_apply_nhwc_bf16": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),

@@ -210,28 +210,10 @@ class MwtRunner:
 
 
 # ------------------------------------------------------------------------------------------ SFE
-def make_backbone(features: nn.Module, device, v2s: bool):
-    """V2-S (torchvision) -> native kernels; anything else (the b0 ablation branches) -> the cuDNN bf16 channels-last copy."""
-    if v2s:
-        return NativeEffNetV2(features, device)
-    return fused_bf16_backbone(features, device)
-
-
-def fused_bf16_backbone(features: nn.Module, device):
-    """Inference copy of an EfficientNet feature extractor: BatchNorm folded into the preceding conv,
-    bf16, channels-last (so the [N,1280,7,7] output is NHWC in memory and the reference's
-    ``rearrange 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)'`` at sfe.py:153 is a free view)."""
-    net = copy.deepcopy(features).eval().float()
-
-    def fuse(mod):
-        for name, child in list(mod.named_children()):
-            fuse(child)
-        if isinstance(mod, nn.Sequential) and len(mod) >= 2 and isinstance(mod[0], nn.Conv2d) and isinstance(mod[1], nn.BatchNorm2d):
-            mod[0] = torch.nn.utils.fuse_conv_bn_eval(mod[0], mod[1])
-            mod[1] = nn.Identity()
-
-    fuse(net)
-    return net.to(device=device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+def make_backbone(net: nn.Module, device, v2s: bool):
+    """Native runner of an EfficientNet feature extractor: torchvision V2-S ``features`` (the dynamic path, sfe.py:111-113)
+    or the efficientnet_pytorch-style b0 module (the two ablation branches, sfe.py:109,148).  There is no library path."""
+    return NativeEffNetV2(net, device) if v2s else NativeEffNetB0(net, device)
 
 
 def _fold_conv_bn(conv, bn):
@@ -455,6 +437,64 @@ class NativeEffNetV2:
         return x
 
 
+class NativeEffNetB0:
+    """``EfficientNet.from_pretrained('efficientnet-b0').extract_features`` (efficientnet_pytorch layout: ``_conv_stem``, ``_bn0``,
+    ``_blocks[i]._expand_conv/_bn0/_depthwise_conv/_bn1/_se_reduce/_se_expand/_project_conv/_bn2``, ``_conv_head``, ``_bn1``;
+    network/sfe.py:109,148) in eval mode on the native kernels: TF-'SAME' stem, 1x1 expand / SE-gated project / head convs on the
+    tcgen05 GEMM kernel, 3x3 / 5x5 depthwise + SiLU + squeeze in ``ewvit_dwconv_nhwc_bf16``, SE gate kernel.  NHWC bf16, BN folded
+    (eps 1e-3 as the module says).  Geometry is read off the module's own convolutions, so the real package and the built-in
+    stand-in (``network/_effnet_b0.py``) are handled alike."""
+
+    def __init__(self, net: nn.Module, device):
+        target = torch.device(device)
+        if any(p.device.type != "cpu" for p in net.parameters()):
+            net = copy.deepcopy(net).to("cpu")
+        bf = torch.bfloat16
+        one = lambda v: int(v[0] if isinstance(v, (tuple, list)) else v)
+        w, b = _fold_conv_bn(net._conv_stem, net._bn0)
+        if tuple(w.shape[1:]) != (3, 3, 3) or one(net._conv_stem.stride) != 2 or w.shape[0] > 32:
+            raise EwvitError("native b0: unexpected stem")
+        self.ops = [("stem", w.contiguous(), b)]
+        for blk in net._blocks:
+            dwc = blk._depthwise_conv
+            mid, k, stride = dwc.weight.shape[0], one(dwc.kernel_size), one(dwc.stride)
+            cin = blk._expand_conv.weight.shape[1] if hasattr(blk, "_expand_conv") else mid
+            cout = blk._project_conv.weight.shape[0]
+            if hasattr(blk, "_expand_conv"):
+                w, b = _fold_conv_bn(blk._expand_conv, blk._bn0)
+                self.ops.append(("conv1", (w.flatten(1) * 0.5).to(bf).contiguous(), b * 0.5, "silu_h", False, False))   # halved: h*tanh(h)+h
+            w, b = _fold_conv_bn(dwc, blk._bn1)
+            self.ops.append(("dw", w.reshape(mid, k * k).t().contiguous(), b, k, stride))
+            self.ops.append(("se", blk._se_reduce.weight.detach().float().flatten(1).contiguous(), blk._se_reduce.bias.detach().float(),
+                             blk._se_expand.weight.detach().float().flatten(1).t().contiguous(), blk._se_expand.bias.detach().float()))
+            w, b = _fold_conv_bn(blk._project_conv, blk._bn2)
+            self.ops.append(("conv1g", w.flatten(1).to(bf).contiguous(), b, None, stride == 1 and cin == cout, True))
+        w, b = _fold_conv_bn(net._conv_head, net._bn1)
+        self.ops.append(("conv1", (w.flatten(1) * 0.5).to(bf).contiguous(), b * 0.5, "silu_h", False, False))
+        self.ops = _to_device(self.ops, target)
+        self.device = target
+
+    def forward(self, frames, norm=None):
+        """fp32 [n,3,H,W] -> bf16 NHWC [n, H/32, W/32, 1280]."""
+        if norm is not None or frames.dtype != torch.float32:
+            raise EwvitError("native b0 takes normalised fp32 frames")
+        x = block_in = pooled = gate = None
+        for i, op in enumerate(self.ops):
+            kind = op[0]
+            with stage(f"b0.{kind}"):
+                if kind == "stem":
+                    x = block_in = ops.stem_conv(frames, op[1], op[2], same_tf=True)
+                elif kind == "conv1":
+                    x = ops.conv_nhwc_bf16(x, op[1], 1, 1, bias=op[2], act=op[3])
+                elif kind == "dw":
+                    x, pooled = ops.dwconv(x, op[1], op[2], op[3], op[4], same_tf=True, pooled=True)
+                elif kind == "se":
+                    gate = ops.se_gate(pooled, op[1], op[2], op[3], op[4], bf16=True)
+                else:       # conv1g: SE gate applied in the operand path, + skip connection
+                    x = block_in = ops.conv1x1_gated(x, gate, op[1], bias=op[2], act=None, residual=block_in if op[4] else None)
+        return x
+
+
 class SfeRunner:
     """Native ``EfficientViT.forward`` after the backbone; ``backbone`` maps fp32 frames to the bf16 NHWC
     feature map.  ``sd`` holds the module's own keys (``patch_to_embedding.weight`` ...)."""
@@ -565,16 +605,10 @@ class SfeRunner:
         return res if res.shape[1] == self.feat_dim else res[:, : self.feat_dim].contiguous()
 
     def features(self, frames, norm=None):
-        """fp32 frames [n,3,H,W] (uint8 with norm on the native backbone) -> bf16 [n, 62720] NHWC-flattened backbone features."""
-        if isinstance(self.backbone, NativeEffNetV2):
-            f = self.backbone.forward(frames, norm=norm)         # NHWC bf16
-            return f.reshape(f.shape[0], -1)
-        if frames.dtype == torch.uint8:
-            raise EwvitError("uint8 frames need the native EfficientNetV2-S backbone")
-        x = frames.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
-        f = self.backbone(x)                                     # [n, C, ph, pw], channels-last memory
-        n = f.shape[0]
-        return f.permute(0, 2, 3, 1).reshape(n, -1)              # view when channels-last
+        """fp32 frames [n,3,H,W] (uint8 with norm on the V2-S backbone) -> bf16 [n, 62720] NHWC-flattened backbone features
+        (the reference's ``rearrange 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)'`` at sfe.py:153 is this flatten for one patch)."""
+        f = self.backbone.forward(frames, norm=norm)             # NHWC bf16
+        return f.reshape(f.shape[0], -1)
 
     def forward(self, frames, pos_index, out=None, norm=None):
         with stage("sfe.backbone"):

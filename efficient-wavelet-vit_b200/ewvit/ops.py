@@ -393,9 +393,12 @@ def conv3x3_c24(x, w, bias, residual=False, out=None):
     return out
 
 
-def stem_conv(x, w, bias, out=None, out_padded=False, norm=None):
-    """fp32 NCHW frames [n,3,h,w] (or uint8 frames with norm=(mean, std)) -> bf16 NHWC [n,h/2,w/2,cout]: conv3x3 s2 + bias + SiLU."""
+def stem_conv(x, w, bias, out=None, out_padded=False, norm=None, same_tf=False):
+    """fp32 NCHW frames [n,3,h,w] (or uint8 frames with norm=(mean, std)) -> bf16 NHWC [n,h/2,w/2,cout]: conv3x3 s2 + bias + SiLU.
+    same_tf: TensorFlow 'SAME' padding (EfficientNet-b0) instead of torchvision's symmetric pad 1."""
     u8 = x.dtype == torch.uint8
+    if same_tf and (u8 or out_padded):
+        raise EwvitError("stem_conv: same_tf is implemented for fp32 frames and the plain output layout")
     if u8:
         _require_cuda(x, "x")
         if not x.is_contiguous() or x.dim() != 4:
@@ -420,7 +423,7 @@ def stem_conv(x, w, bias, out=None, out_padded=False, norm=None):
             check(load().ewvit_stem_conv_u8_fwd(x.data_ptr(), norm[0].data_ptr(), norm[1].data_ptr(), n, h, wd, w.data_ptr(), bias.data_ptr(),
                                                 cout, out.data_ptr(), int(out_padded), _stream()), "ewvit_stem_conv_u8_fwd")
         else:
-            fn = load().ewvit_stem_conv_padded_fwd if out_padded else load().ewvit_stem_conv_fwd
+            fn = load().ewvit_stem_conv_same_fwd if same_tf else load().ewvit_stem_conv_padded_fwd if out_padded else load().ewvit_stem_conv_fwd
             check(fn(x.data_ptr(), n, h, wd, w.data_ptr(), bias.data_ptr(), cout, out.data_ptr(), _stream()), "ewvit_stem_conv_fwd")
     return out
 

@@ -142,7 +142,7 @@ class EfficientViT(NativeMixin, nn.Module):
     # ---- native path
     def _build_runner(self):
         from ewvit.engine import SfeRunner, make_backbone
-        feats = self.efficient_net.features if self.selected_efficient_net != 0 else _B0Features(self.efficient_net)
+        feats = self.efficient_net.features if self.selected_efficient_net != 0 else self.efficient_net
         dev = self.pos_embedding.device
         backbone = make_backbone(feats, dev, v2s=self.selected_efficient_net != 0)
         sd = {k: v for k, v in self.state_dict().items() if not k.startswith("efficient_net.")}
@@ -160,17 +160,6 @@ class EfficientViT(NativeMixin, nn.Module):
                 return out
             return out.clone().view(n, -1, 1, 1)
         return self._forward_torch(img)
-
-
-class _B0Features(nn.Module):
-    """Adapter so the b0 backbone exposes the ``features(img)`` call the runner folds and casts."""
-
-    def __init__(self, net):
-        super().__init__()
-        self.net = net
-
-    def forward(self, x):
-        return self.net.extract_features(x)
 
 
 def _v2s_weights():

@@ -262,7 +262,11 @@ EWVIT_API int ewvit_conv3x3_c24_fwd(const void *x, const void *w, int wk, const 
  * fp32 -> bf16 / NCHW -> NHWC conversion).  x [n,3,h,wd] fp32, w [cout,3,3,3] fp32, y [n,ho,wo,cout] bf16. */
 EWVIT_API int ewvit_stem_conv_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
                                   void *y, void *stream);
-/* Same, writing the interior of a padded-flat output y [n, ho+2, wo+2, cout] (the caller zeroes the border once). */
+/* Same with TensorFlow 'SAME' padding (efficientnet_pytorch's Conv2dStaticSamePadding, EfficientNet-b0 stem 3 -> 32,
+ * network/sfe.py:109,148): on even sizes the only padding is one zero row/column at the bottom/right. */
+EWVIT_API int ewvit_stem_conv_same_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
+                                       void *y, void *stream);
+/* Same as ewvit_stem_conv_fwd, writing the interior of a padded-flat output y [n, ho+2, wo+2, cout] (the caller zeroes the border once). */
 EWVIT_API int ewvit_stem_conv_padded_fwd(const float *x, int n, int h, int wd, const float *w, const float *bias, int cout,
                                          void *y, void *stream);
 /* Stem from uint8 frames x [n,3,h,wd] with the same on-load normalisation as ewvit_dwt3_haar_u8_fwd (the conv's zero

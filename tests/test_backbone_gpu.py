@@ -150,6 +150,17 @@ def test_conv3x3_stride2_from_padded_input(ops, cin, cout, out_padded, hw):
         _close(got.permute(0, 3, 1, 2), ref)
 
 
+def test_stem_tf_same_padding(ops):
+    """EfficientNet-b0 stem: 3 -> 32, 3x3 stride 2 with TensorFlow 'SAME' padding (zero row/column at the bottom/right only)."""
+    x = seeded_randn((2, 3, 224, 224), 8)
+    wt = seeded_randn((32, 3, 3, 3), 9) * 27 ** -0.5
+    b = seeded_randn((32,), 10)
+    ref = F.silu(F.conv2d(F.pad(x, (0, 1, 0, 1)), wt, b, stride=2))
+    got = ops.stem_conv(x.cuda(), wt.cuda().contiguous(), b.cuda(), same_tf=True)
+    assert got.shape == (2, 112, 112, 32)
+    _close(got.permute(0, 3, 1, 2), ref, tol=1e-3)
+
+
 def test_stem_padded(ops):
     x = seeded_randn((2, 3, 224, 224), 8)
     wt = seeded_randn((24, 3, 3, 3), 9) * 27 ** -0.5

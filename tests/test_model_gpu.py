@@ -8,7 +8,8 @@ Floating point, bf16 tensor-core operands with fp32 accumulation: the stated tol
 * TOL_FRAME = 3e-2: outputs that sit behind the ~170-layer bf16 EfficientNet chain and are NOT averaged over a full
   video -- per-frame `_process_frame` outputs, per-video means over <= 8 frames and the logits computed from them
   (measured 7e-3..2.6e-2; the backbone feature map itself is within 2.9e-2 of torchvision fp32, cuDNN's own bf16 path
-  within 3.9e-2);
+  within 3.9e-2); TOL_B0 = 4e-2 for the same kind of outputs behind the EfficientNet-b0 chain of the ablation branches
+  (16 SE-gated MBConv blocks with bf16 gates: per-frame features measured 3.1e-2, 4-5-frame logits of `sfe_only` 3.1e-2);
 * 1e-4 for the fp32-only DAMA tail; and identical
 real/fake decisions (sign of the logit) wherever |logit_ref| exceeds the tolerance."""
 import pytest
@@ -21,6 +22,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1.5e-2
 TOL_FRAME = 3e-2
+TOL_B0 = 4e-2
 
 
 def rel_err(got, ref):
@@ -124,13 +126,20 @@ def test_mwt_module_matches_runner_and_ragged_batch(detector, dama_sd):
     check("MWT module", got1, ref)
 
 
-def test_backbone_bf16(detector, dama_sd, frames, golden):
+def test_native_b0_backbone(detector, manifest, frames, golden):
+    """EfficientNet-b0 `extract_features` on the native kernels (TF-SAME stem, 3x3 / 5x5 depthwise, SE-gated project convs) vs the
+    functional fp32 oracle (oracle/effnet_b0.py) and the golden features of the module the reference ran on."""
+    from _weights import state_dict_from_manifest
     from ewvit import engine
-    bb = engine.fused_bf16_backbone(detector.dama.sfe.efficient_net.features, "cuda")
+    from oracle.effnet_b0 import extract_features
+    sd = state_dict_from_manifest(manifest, seed=0, prefixes=("sfe.efficient_net.",))
+    bb = engine.NativeEffNetB0(detector.sfe.efficient_net, "cuda")
     with torch.no_grad():
-        f = bb(frames.cuda().to(dtype=torch.bfloat16, memory_format=torch.channels_last))
-        ref = O.backbone_v2s_features(dama_sd, "dama.sfe.efficient_net.", frames)
-    check("EfficientNetV2-S features (bf16 cuDNN, BN folded)", f, ref, 6e-2)
+        f = bb.forward(frames.cuda())
+        ref = extract_features(sd, "sfe.efficient_net.", frames)
+    assert f.shape == (2, 7, 7, 1280)
+    check("EfficientNet-b0 features (native)", f.permute(0, 3, 1, 2), ref, TOL_B0)
+    check("EfficientNet-b0 feature means vs reference golden", f.float().mean(dim=(1, 2)), golden["b0_feat_mean"], TOL_B0)
 
 
 def test_sfe_head_on_identical_features(dama_sd, sd_cuda, frames):
@@ -268,10 +277,10 @@ def test_detector_ablation_modes_match_reference_golden(detector, ablation_sd, g
     assert out["model"] == mode and sorted(out) == sorted(k for k in g if k not in ("seed", "shape", "batch_size"))
     assert detector.ablation == mode
     for k in (("logits",) if mode == "sfe_only" else ("sfe", "mwt", "logits")):
-        tol_k = TOL if k == "mwt" or (k == "logits" and mode == "sfe_mwt") else TOL_FRAME    # b0 chain, means over 4-5 frames
+        tol_k = TOL if k == "mwt" or (k == "logits" and mode == "sfe_mwt") else TOL_B0       # b0 chain, means over 4-5 frames
         check(f"{mode}/{tag}[{k}] vs oracle", out[k], ref[k], tol_k)
         check(f"{mode}/{tag}[{k}] vs reference golden", out[k], g[k], tol_k)
-    tol = TOL_FRAME * float(g["logits"].abs().max())
+    tol = TOL_B0 * float(g["logits"].abs().max())
     decided = g["logits"].abs() > tol
     assert torch.equal((out["logits"].cpu() >= 0)[decided], (g["logits"] >= 0)[decided])
 
@@ -282,8 +291,8 @@ def test_sfe_b0_module_both_output_modes(detector, ablation_sd, frames, golden):
         y = detector.sfe(frames.cuda())
         c = detector.sfe_cls(frames.cuda())
     assert y.shape == (2, 128, 1, 1) and c.shape == (2, 1)
-    check("sfe (b0, feature_map) vs reference golden", y, golden["sfe_b0_out"], 4e-2)      # per frame, cuDNN bf16 b0 chain
-    check("sfe_cls (b0, cls) vs reference golden", c, golden["sfe_cls_out"], 4e-2)
+    check("sfe (b0, feature_map) vs reference golden", y, golden["sfe_b0_out"], TOL_B0)      # per frame, 80-layer bf16 b0 chain
+    check("sfe_cls (b0, cls) vs reference golden", c, golden["sfe_cls_out"], TOL_B0)
 
 
 def test_full_shape_config4_eval_scoring_call(detector, dama_sd):
