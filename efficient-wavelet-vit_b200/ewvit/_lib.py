@@ -55,6 +55,7 @@ SIGNATURES = {
     "ewvit_mwt_head_mma_fwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "ewvit_mwt_upsample_fwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "ewvit_mwt_head_conv_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P]),
+    "ewvit_binary_metrics_fwd": (c_int, [P, P, c_int, P, P]),
     "ewvit_debug_set_trace": (c_int, [P]),
     "ewvit_debug_set_flags": (c_int, [c_int]),
     "ewvit_video_head_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P, P, P, P, P, c_int, P, P]),

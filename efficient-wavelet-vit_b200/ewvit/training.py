@@ -42,10 +42,32 @@ def combined_loss(outputs, labels, epoch, max_epochs, alpha=0.25, gamma=2.0):
     the epochs."""
     labels = labels.view(-1, 1).float()
     cls = binary_focal_loss(outputs["logits"], labels, alpha, gamma)
-    if epoch < 0.2 * max_epochs:
-        return cls
+    if epoch < 0.2 * max_epochs or "space" not in outputs:      # sfe_only / sfe_mwt return no branch features: classification loss only
+        return cls                                              # (ablation.py:70-76, eval.py:158-160)
     lam = min(1.0, (epoch - 0.2 * max_epochs) / (0.5 * max_epochs))
     return cls + lam * orthogonal_loss(outputs["space"], outputs["freq"])
+
+
+def freeze_unused_(model, ablation):
+    """Switch off ``requires_grad`` for every parameter outside the ablation mode's path (dynamic: ``dama`` + ``classifier``;
+    sfe_only: ``sfe_cls``; sfe_mwt: ``sfe`` + ``mwt`` + ``fusion_gate`` + ``classifier`` -- model.py:83-161), keeping the
+    reference's frozen backbone prefix (sfe.py:115-119).  DistributedDataParallel then registers exactly the tensors that
+    receive gradients, so no ``find_unused_parameters`` graph walk is needed per step.  Returns the number of trainable
+    scalars (= fp32 gradient elements all-reduced per optimizer step)."""
+    used = {"dynamic": ("dama.", "classifier."), "sfe_only": ("sfe_cls.",),
+            "sfe_mwt": ("sfe.", "mwt.", "fusion_gate.", "classifier.")}[ablation]
+    total = 0
+    for name, p in model.named_parameters():
+        on_path = name.startswith(used)
+        if ablation == "sfe_only" and name.startswith("sfe_cls.feat_map."):
+            on_path = False                      # cls mode returns mlp_head(token 0): feat_map is never evaluated (sfe.py:163-166)
+        if ablation in ("dynamic", "sfe_mwt") and (name.startswith("dama.sfe.mlp_head.") or name.startswith("sfe.mlp_head.")):
+            on_path = False                      # feature-map mode never evaluates mlp_head (sfe.py:168-173)
+        if not on_path:
+            p.requires_grad_(False)
+        if p.requires_grad:
+            total += p.numel()
+    return total
 
 
 def train_step(model, micro_batches, optimizer, ablation="dynamic", batch_size=8, epoch=0, max_epochs=1, alpha=0.25, gamma=2.0):

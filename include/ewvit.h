@@ -320,6 +320,13 @@ EWVIT_API int ewvit_debug_set_trace(void *device_buffer);
  * backbone epilogues; 512: MWT epilogue does no work at all. */
 EWVIT_API int ewvit_debug_set_flags(int flags);
 
+/* Binary classification metrics of the evaluation loop (eval.py:79-94,174-192; scikit-learn definitions) computed on the device
+ * from the gathered per-video scores: scores [n] fp32 probabilities (sigmoid of the logits), labels [n] int32 (0 real / 1 fake),
+ * n <= 8192.  out [12] fp32: 0 auc (roc_auc_score), 1 eer, 2 eer_threshold (calculate_eer on roc_curve with its default
+ * drop_intermediate), 3 accuracy, 4 precision, 5 recall, 6 f1 (threshold 0.5, 0 when undefined), 7 average precision,
+ * 8..11 confusion matrix tn, fp, fn, tp.  auc / eer / ap are NaN when only one class is present. */
+EWVIT_API int ewvit_binary_metrics_fwd(const float *scores, const int *labels, int n, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -175,6 +175,54 @@ with torch.no_grad():
     cat = seeded_randn((3, 256, 1, 1), 51)
     gold["fusion_gate"] = {"x": small(cat), "y": small(model.dama.fusion_gate(cat))}
 
+# ---- f-2: ONE TRAINING MICRO-STEP of the unmodified reference (train.py:93-111 semantics): train mode, BatchNorm batch
+#      statistics per chunk of B*batch_size frames (dama.py:179-186), every Dropout / StochasticDepth probability set to 0 so the
+#      step is deterministic, loss = BinaryFocalLoss (config/focal_loss.py) + orthogonal loss at lambda = 1 (train.py:55-91)
+from config.focal_loss import BinaryFocalLoss  # noqa: E402  (the reference's own module)
+
+fill_module_(model, seed=0)
+model.train()
+for m in model.modules():
+    if isinstance(m, torch.nn.Dropout) or type(m).__name__ == "StochasticDepth":
+        m.p = 0.0
+tx = seeded_randn((2, 4, 3, 224, 224), 71)
+ty = torch.tensor([0.0, 1.0])
+model.zero_grad(set_to_none=True)
+tout = model(tx, batch_size=2, ablation="dynamic")
+
+
+def _orth(space, freq):                                   # train.py:55-67
+    d = space.shape[1]
+    sp, fq = torch.nn.functional.normalize(space, p=2, dim=1), torch.nn.functional.normalize(freq, p=2, dim=1)
+    off = torch.mm(sp.T, fq) * (1 - torch.eye(d))
+    return torch.norm(off, p="fro") ** 2 / (d * (d - 1))
+
+
+cls_loss = BinaryFocalLoss()(tout["logits"], ty.view(-1, 1))
+orth_loss = _orth(tout["space"], tout["freq"])
+(cls_loss + orth_loss).backward()
+named = dict(model.named_parameters())
+GRAD_KEYS = ["classifier.3.weight", "classifier.0.bias", "dama.gate_net.5.weight", "dama.cross_att.layers.1.3.to_q.weight",
+             "dama.fusion_gate.0.bias", "dama.sfe.feat_map.0.weight", "dama.sfe.patch_to_embedding.bias",
+             "dama.sfe.transformer.layers.0.0.fn.to_qkv.weight", "dama.mwt.freq_pool.1.weight", "dama.mwt.multiscale_fusion.0.bias",
+             "dama.mwt.hf_conv.seperate.1.0.weight", "dama.sfe.efficient_net.features.7.0.weight",
+             "dama.sfe.efficient_net.features.2.0.block.0.0.weight"]
+BUF_KEYS = ["dama.mwt.freq_conv.1.running_mean", "dama.mwt.freq_conv.1.running_var", "dama.mwt.freq_conv.1.num_batches_tracked",
+            "dama.fusion_gate.1.running_var", "dama.sfe.efficient_net.features.7.1.running_mean"]
+sdt = model.state_dict()
+gold["train_step"] = {
+    "seed": 71, "shape": [2, 4, 3, 224, 224], "batch_size": 2, "labels": ty.clone(),
+    "logits": small(tout["logits"]), "fused": small(tout["fused"]), "space": small(tout["space"]), "freq": small(tout["freq"]),
+    "cls_loss": float(cls_loss), "orth_loss": float(orth_loss),
+    "grads": {k: small(named[k].grad if named[k].grad.numel() <= 4096 else named[k].grad.flatten()[:4096]) for k in GRAD_KEYS},
+    "grad_norms": {k: float(named[k].grad.norm()) for k in GRAD_KEYS},
+    "no_grad": [k for k in ("mwt.freq_conv.0.weight", "sfe.feat_map.0.weight", "sfe_cls.mlp_head.0.weight", "fusion_gate.0.weight")
+                if named[k].grad is None],
+    "buffers": {k: small(sdt[k]) for k in BUF_KEYS},
+}
+print("train step: cls", float(cls_loss), "orth", float(orth_loss), "logits", tout["logits"].flatten().tolist())
+model.eval()
+
 torch.save(gold, os.path.join(HERE, "ewvit_golden.pt"))
 print("wrote", os.path.join(HERE, "ewvit_golden.pt"), os.path.getsize(os.path.join(HERE, "ewvit_golden.pt")), "bytes")
 print("logits (dynamic, K=5):", out["logits"].flatten().tolist())

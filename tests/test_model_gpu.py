@@ -351,6 +351,56 @@ def test_other_dama_dims():
             m64(x.cuda(), 2, "dynamic")
 
 
+def test_training_micro_step_matches_reference_golden(golden):
+    """Row f-2 pinned to the reference: ONE training micro-step (train mode, BatchNorm batch statistics per chunk of B*batch_size
+    frames, dropout / stochastic depth probabilities 0, focal + orthogonality loss, backward) of the drop-in modules on the GPU
+    against the same step of the UNMODIFIED reference on the CPU (tests/golden/make_golden.py): outputs, both loss terms, a
+    spread of parameter gradients (classifier, DAMA, ViT, MWT, backbone), updated BatchNorm buffers, and which parameters get no
+    gradient.  fp32 on both sides (TF32 off): tolerance 2e-3 of the tensor's max (different conv algorithms / reduction orders
+    through ~170 BatchNorm layers with batch statistics of 4 frames)."""
+    from _weights import fill_module_
+    from ewvit.training import binary_focal_loss, orthogonal_loss
+    from network.model import DeepfakeDetector
+    g = golden["train_step"]
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        m = DeepfakeDetector(3, 128, batch_size=2)
+        fill_module_(m, seed=0)
+        m = m.cuda().train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout) or type(mod).__name__ == "StochasticDepth":
+                mod.p = 0.0
+        x = seeded_randn(tuple(g["shape"]), g["seed"]).cuda()
+        out = m(x, g["batch_size"], "dynamic")
+        cls = binary_focal_loss(out["logits"], g["labels"].cuda().view(-1, 1))
+        orth = orthogonal_loss(out["space"], out["freq"])
+        (cls + orth).backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    for k in ("logits", "fused", "space", "freq"):
+        check(f"train step [{k}]", out[k], g[k], 2e-3)
+    cls, orth = cls.detach(), orth.detach()
+    assert abs(float(cls) - g["cls_loss"]) <= 2e-3 * abs(g["cls_loss"]) + 1e-7, (float(cls), g["cls_loss"])
+    assert abs(float(orth) - g["orth_loss"]) <= 1e-2 * abs(g["orth_loss"]) + 1e-7, (float(orth), g["orth_loss"])
+    named = dict(m.named_parameters())
+    for k, ref in g["grads"].items():
+        if g["grad_norms"][k] < 1e-4:          # conv biases in front of a train-mode BatchNorm: the gradient is rounding noise
+            continue
+        got = named[k].grad
+        got = got if got.numel() <= 4096 else got.flatten()[:4096]
+        check(f"train step grad[{k}]", got, ref, 1e-2)
+    for k in g["no_grad"]:
+        assert named[k].grad is None, k
+    sd = m.state_dict()
+    for k, ref in g["buffers"].items():
+        if ref.dtype == torch.int64:
+            assert int(sd[k]) == int(ref), k
+        else:
+            check(f"train step buffer[{k}]", sd[k], ref, 2e-3)
+
+
 def test_training_step_focal_loss_accumulation():
     """BASELINE configs[4], one rank: two accumulated micro-steps (forward + backward through the PyTorch composition with the
     native Haar kernel and its adjoint, focal + orthogonality loss) and one Adam step.  Gradients reach the dynamic path
