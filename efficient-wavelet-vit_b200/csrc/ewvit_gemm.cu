@@ -26,7 +26,7 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int kStages = 12;          // barrier slots; the ring depth actually used is GemmParams::stages
-constexpr int kAccStages = 2;
+constexpr int kMaxAccStages = 4;
 constexpr int kTileBytes = BM * BK * 2;        // 16 KiB
 enum { EPI_CONV = 0, EPI_LINEAR = 1, EPI_PARTIAL = 2, EPI_BB = 3 };
 constexpr int kBuilderWarps = 8;                // A_IM2COL / A_SCALED only: 256 threads assemble or rescale the A tiles in shared memory
@@ -52,8 +52,15 @@ struct Cfg {
     static constexpr int kEpiGroups = kEpiWarps / 4;
     static constexpr int kHalves = kEpiGroups / 2;                       // column halves per accumulator stage
     static constexpr int kThreads = 64 + 32 * kEpiWarps + (kBuilder ? 32 * kBuilderWarps : 0);
-    static constexpr int kStagingBytes = kEpiWarps * kStgBytes;          // per-warp staging buffers of the epilogue
-    static constexpr int kOperandBytes = (kWideEpi ? 160 : kBuilder ? 192 : 200) * 1024;  // operand stages (+ halo buffers)
+    // per-warp staging buffers of the epilogue; the MWT conv epilogue double-buffers them (the TMA store of chunk c reads
+    // buffer c & 1 while chunk c + 1 is converted and staged: a single buffer made every chunk wait for the previous store's read)
+    static constexpr int kStgBufs = kEpi == EPI_CONV ? 2 : 1;
+    // TMEM accumulator stages.  The MWT convs (128 columns per tile) use all 512 columns = 4 stages: the two epilogue groups have the
+    // throughput (one tile per ~2500 cycles each against one per ~2200 of the issuer) but with two stages the issuer still waited
+    // 300-900 cycles per tile for the group two tiles back; four stages absorb that latency
+    static constexpr int kAccStages = kEpi == EPI_CONV ? 4 : 2;
+    static constexpr int kStagingBytes = kEpiWarps * kStgBytes * kStgBufs;
+    static constexpr int kOperandBytes = (kWideEpi ? 160 : kBuilder ? 192 : kEpi == EPI_CONV ? 184 : 200) * 1024;  // operand stages (+ halo buffers)
     static constexpr int kGateOff = kOperandBytes + kStagingBytes;       // builder kernels: staged SE gates
     static constexpr int kPayloadBytes = kGateOff + (kBuilder ? kGateBytes : 0);  // barriers live right behind
     static constexpr int kSmemBytes = kPayloadBytes + 1024 /*align slack*/ + 512 /*barriers*/;
@@ -102,6 +109,7 @@ struct GemmParams {
     int a_gate_bf16;
     int a_hw;              // rows (pixels) per frame
     int a_k;               // K = row pitch of A and of the gate
+    int pair;              // flat3 convs: CTA pairs on cta_group::2 (the B tiles in shared memory hold kBN / 2 filter rows)
     int a_gate_smem;       // the gates of a tile's frames are staged in shared memory once per tile (bf16 gates, <= kGateFrames frames per tile)
     int flat3;           // A_FLAT 3x3 conv, "row-shared" taps: one ring slot = (dy, channel chunk) holds ONE window of
                          // kFlat3Rows activation rows and the three weight tiles of dx = 0,1,2; the three A operands are the
@@ -129,8 +137,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // 16-byte writes are conflict-free) and one lane issues a bulk tensor store.  The LSU never sees the scattered
 // row-per-lane pattern (32 cache lines x 16 bytes per STG measured ~15k cycles per 128x256 tile), stores drain
 // asynchronously while the warp computes the next chunk, and rows/columns outside the tensor are clipped by TMA.
+template <int kPending = 0>
 __device__ __forceinline__ void stage_chunk_bf16(uint32_t stg, int lane, const uint32_t (&pk)[16]) {
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has finished reading the buffer
+    // the store that last used THIS buffer has finished reading it (kPending = stores allowed to be still in flight)
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
     __syncwarp();
     const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
 #pragma unroll
@@ -170,7 +180,12 @@ __device__ __forceinline__ bool decode_tile(const GemmParams &p, int w, int &m_t
 // kFast (EPI_BB only): 0 = generic epilogue (runtime activation / residual switches), 1 = SiLU on pre-halved operands
 // without residual, 2 = no activation (+ optional bf16 residual).  The specialised bodies are ONE basic block per 32-column chunk
 // (32 independent values per lane for the scheduler) -- the generic one branches every 8 columns and ran at ~1/3 IPC.
-template <int kEpi, bool kBuilder, int kBN, int kFast = 0>
+// kPair (MWT 3x3 convs on the row-shared-tap path only): CTA pairs on cta_group::2.  The two CTAs of a 2-CTA cluster take two
+// consecutive 128-row tiles; each loads its own activation window and HALF of every weight tile (64 of the 128 filters), the
+// leader issues M = 256 MMAs for both and the completions are multicast onto both CTAs' barriers.  Per MMA a CTA's tensor core
+// reads 4 KB of A and 2 KB of B from its shared memory instead of 4 + 4, and the ring slot shrinks from 65 KB to 41 KB
+// (multiscale conv: 3 -> 4 stages; fusion conv with resident weights: 72 KB instead of 144 KB resident, 3 -> 7 windows in flight).
+template <int kEpi, bool kBuilder, int kBN, int kFast = 0, bool kPair = false>
 __global__ void __launch_bounds__(Cfg<kEpi, kBuilder>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -179,9 +194,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int kEpiWarps = Cfg<kEpi, kBuilder>::kEpiWarps, kHalves = Cfg<kEpi, kBuilder>::kHalves;
     constexpr int kOperandBytes = Cfg<kEpi, kBuilder>::kOperandBytes;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + Cfg<kEpi, kBuilder>::kPayloadBytes);
+    constexpr int kAccStages = Cfg<kEpi, kBuilder>::kAccStages;
     unsigned long long *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages,
-                       *tempty = bars + 2 * kStages + kAccStages;
-    unsigned long long *hfull = bars + 2 * kStages + 2 * kAccStages, *hempty = hfull + kMaxHalo;
+                       *tempty = bars + 2 * kStages + kMaxAccStages;
+    unsigned long long *hfull = bars + 2 * kStages + 2 * kMaxAccStages, *hempty = hfull + kMaxHalo;
     unsigned long long *bres_bar = hempty + kMaxHalo;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bres_bar + 1);
     const uint32_t kBTileB = (uint32_t)p.b_tile_bytes;    // B tile: b_rows x 64 bf16 (b_rows = kBN, or the 16-aligned N of a single column tile)
@@ -192,6 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler, too
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = kPair ? ewvit::cluster_ctarank() : 0u;   // 0 = leader of the CTA pair (issues the MMAs)
     const int nstages = p.stages;
     const uint32_t kStageB = (uint32_t)p.stage_bytes;    // A tile + B tile (A only when B is resident)
 
@@ -204,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < kAccStages; ++a) {
             ewvit::mbar_init(ewvit::smem_u32(&tfull[a]), 1);
-            ewvit::mbar_init(ewvit::smem_u32(&tempty[a]), kEpiWarps / 2);
+            ewvit::mbar_init(ewvit::smem_u32(&tempty[a]), kPair ? kEpiWarps : kEpiWarps / 2);   // pair: the epilogue warps of BOTH CTAs
         }
         ewvit::mbar_init(ewvit::smem_u32(bres_bar), 1);
         for (int a = 0; a < kMaxHalo; ++a) {
@@ -214,15 +231,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ewvit::mbar_fence_init();
     }
     if (warp == 1) {
-        ewvit::tmem_alloc(ewvit::smem_u32(tmem_slot), kTmemColsT);
-        ewvit::tmem_relinquish();
+        if (kPair) {
+            ewvit::tmem_alloc_pair(ewvit::smem_u32(tmem_slot), kTmemColsT);
+            ewvit::tmem_relinquish_pair();
+        } else {
+            ewvit::tmem_alloc(ewvit::smem_u32(tmem_slot), kTmemColsT);
+            ewvit::tmem_relinquish();
+        }
     }
     ewvit::tc_fence_before();
-    __syncthreads();
+    if (kPair) ewvit::cluster_sync_all();     // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    else __syncthreads();
     ewvit::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int total_work = p.tiles_m * p.tiles_n * p.splits;
+    // pair mode: work items are PAIRS of row tiles; cluster c takes items c, c + #clusters, ...; CTA rank r the r-th tile of the pair
+    const int tiles_m2 = (p.tiles_m + 1) >> 1;
+    const int pair_work = tiles_m2 * p.tiles_n;
+    const int w_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int w_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int w_total = kPair ? pair_work : total_work;
+    auto decode = [&](int w, int &m_t, int &n_t, int &sp) -> bool {
+        if (kPair) {
+            m_t = 2 * (w % tiles_m2) + (int)cta_rank;      // may be one past the last tile (odd tile count): TMA zero-fills / clips it
+            n_t = w / tiles_m2;
+            sp = 0;
+            return true;
+        }
+        return decode_tile(p, w, m_t, n_t, sp);
+    };
     const uint32_t smem_base = ewvit::smem_u32(smem);
 
     // The two issuing roles run WARP-UNIFORM loops (all 32 lanes track the same counters and poll the same
@@ -238,16 +276,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int nb = p.flat3 ? 3 * p.num_kb : p.num_kb;    // flat3: num_kb counts (dy, chunk) slots of three taps each
             if (ewvit::elect_one()) {
                 const uint32_t bb = ewvit::smem_u32(bres_bar);
-                ewvit::mbar_expect_tx(bb, (uint32_t)(nb * kBTileB));
-                for (int kb = 0; kb < nb; ++kb)
-                    ewvit::tma_load_2d(smem_base + p.bres_off + kb * kBTileB, &tmB, kb * BK, 0, bb);
+                if (kPair) {           // each CTA keeps ITS half of the filter rows; both halves count on the leader's barrier
+                    if (cta_rank == 0) ewvit::mbar_expect_tx(bb, (uint32_t)(2 * nb * kBTileB));
+                    for (int kb = 0; kb < nb; ++kb)
+                        ewvit::tma_load_2d_pair(smem_base + p.bres_off + kb * kBTileB, &tmB, kb * BK, (int)cta_rank * (kBN / 2), bb);
+                } else {
+                    ewvit::mbar_expect_tx(bb, (uint32_t)(nb * kBTileB));
+                    for (int kb = 0; kb < nb; ++kb)
+                        ewvit::tma_load_2d(smem_base + p.bres_off + kb * kBTileB, &tmB, kb * BK, 0, bb);
+                }
             }
             __syncwarp();
         }
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tt) {
+        for (int w = w_first; w < w_total; w += w_step, ++tt) {
             if (lane == 0) EWVIT_TRACE(0, tt, 0);
             int m_t, n_t, sp;
-            if (!decode_tile(p, w, m_t, n_t, sp)) continue;
+            if (!decode(w, m_t, n_t, sp)) continue;
             const int kb0 = sp * p.kb_per_split;
             const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             int tx = 0, ty = 0, img = 0;
@@ -292,7 +336,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     ewvit::mbar_wait(ewvit::smem_u32(&empty[stage]), phase ^ 1);
                     const uint32_t bar = ewvit::smem_u32(&full[stage]);
                     const uint32_t a_dst = smem_base + stage * kStageB;
-                    if (ewvit::elect_one()) {
+                    if (kPair) {
+                        if (ewvit::elect_one()) {
+                            // both CTAs' loads of this slot complete on the LEADER's full barrier (it expects the bytes of the pair)
+                            if (cta_rank == 0) ewvit::mbar_expect_tx(bar, 2 * kStageB);
+                            ewvit::tma_load_2d_pair(a_dst, &tmA, ch * BK, m_t * BM + p.tap_a0[dy * 3], bar);
+                            if (!p.b_res) {
+#pragma unroll
+                                for (int dx = 0; dx < 3; ++dx)
+                                    ewvit::tma_load_2d_pair(a_dst + kFlat3ABytes + dx * kBTileB, &tmB, ((dy * 3 + dx) * p.chunks_per_tap + ch) * BK,
+                                                            n_t * kBN + (int)cta_rank * (kBN / 2), bar);
+                            }
+                        }
+                    } else if (ewvit::elect_one()) {
                         ewvit::mbar_expect_tx(bar, kStageB);
                         ewvit::tma_load_2d(a_dst, &tmA, ch * BK, m_t * BM + p.tap_a0[dy * 3], bar);
                         if (!p.b_res) {
@@ -327,23 +383,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) EWVIT_TRACE(0, tt, 1);
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
+        // ------------------------------------------------------------ MMA issuer (pair mode: the leader CTA only)
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         int tt = 0;
-        if (p.b_res) ewvit::mbar_wait(ewvit::smem_u32(bres_bar), 0);
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tt) {
+        if (p.b_res && cta_rank == 0) ewvit::mbar_wait(ewvit::smem_u32(bres_bar), 0);
+        for (int w = w_first; w < w_total && cta_rank == 0; w += w_step, ++tt) {
             if (lane == 0) EWVIT_TRACE(1, tt, 0);
             int m_t, n_t, sp;
-            if (!decode_tile(p, w, m_t, n_t, sp)) continue;
+            if (!decode(w, m_t, n_t, sp)) continue;
             (void)m_t;
             const int kb0 = sp * p.kb_per_split;
             const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             // columns past N are zero-filled B rows: shrink the MMA's N to the valid part (multiple of 16)
             const int n_valid = min(kBN, p.N - n_t * kBN);
-            const uint32_t idesc = ewvit::umma_idesc_bf16(BM, (uint32_t)((n_valid + 15) & ~15));
+            const uint32_t idesc = ewvit::umma_idesc_bf16(kPair ? 2 * BM : BM, (uint32_t)((n_valid + 15) & ~15));
             ewvit::mbar_wait(ewvit::smem_u32(&tempty[acc]), acc_phase ^ 1);
             ewvit::tc_fence_after();
             if (lane == 0) EWVIT_TRACE(1, tt, 1);
@@ -368,12 +424,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const int dy = kb / p.chunks_per_tap, ch = kb - dy * p.chunks_per_tap;
                             const uint64_t bd = ewvit::umma_desc_sw128(
                                 p.b_res ? smem_base + p.bres_off + ((dy * 3 + dx) * p.chunks_per_tap + ch) * kBTileB : a_addr + kFlat3ABytes + dx * kBTileB);
-                            ewvit::umma_bf16(d_tmem, ad, bd, idesc, (dx > 0 || kb > kb0) ? 1u : 0u);
-                            ewvit::umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-                            ewvit::umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-                            ewvit::umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                            if (kPair) {
+                                ewvit::umma_bf16_pair(d_tmem, ad, bd, idesc, (dx > 0 || kb > kb0) ? 1u : 0u);
+                                ewvit::umma_bf16_pair(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                                ewvit::umma_bf16_pair(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                                ewvit::umma_bf16_pair(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                            } else {
+                                ewvit::umma_bf16(d_tmem, ad, bd, idesc, (dx > 0 || kb > kb0) ? 1u : 0u);
+                                ewvit::umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                                ewvit::umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                                ewvit::umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                            }
                         }
-                        ewvit::umma_commit(ebar);
+                        if (kPair) ewvit::umma_commit_pair(ebar);      // frees this slot in BOTH CTAs
+                        else ewvit::umma_commit(ebar);
                     }
                 } else if (ewvit::elect_one()) {
                     // advancing 16 K-elements = 32 bytes = +2 in the descriptor's (address >> 4) field
@@ -386,7 +450,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
-            if (ewvit::elect_one()) ewvit::umma_commit(ewvit::smem_u32(&tfull[acc]));   // accumulator ready for the epilogue
+            if (ewvit::elect_one()) {                                                    // accumulator ready for the epilogue(s)
+                if (kPair) ewvit::umma_commit_pair(ewvit::smem_u32(&tfull[acc]));
+                else ewvit::umma_commit(ewvit::smem_u32(&tfull[acc]));
+            }
             __syncwarp();
             if (lane == 0) EWVIT_TRACE(1, tt, 3);
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -686,18 +753,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int half = grp >> 1;
         const int r = q * 32 + lane;            // row of the tile owned by this thread
         const int gtid = (threadIdx.x - 64) & 127;
-        const int acc = grp & 1;
-        float *g_scale = s_scale + acc * kBN, *g_shift = s_shift + acc * kBN;
+        const int grp2 = grp & 1;               // which of every two consecutive tiles this group drains
+        float *g_scale = s_scale + grp2 * kBN, *g_shift = s_shift + grp2 * kBN;
         constexpr int kColsPerGroup = kBN / kHalves;
-        const uint32_t stg = smem_base + kOperandBytes + (uint32_t)(warp - 2) * kStgBytes;
-        uint32_t acc_phase = 0;
+        const uint32_t stg = smem_base + kOperandBytes + (uint32_t)(warp - 2) * kStgBytes * Cfg<kEpi, kBuilder>::kStgBufs;
         int cur_nt = -1;
         int it = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
-            if ((it & 1) != acc) continue;
+        for (int w = w_first; w < w_total; w += w_step, ++it) {
+            if ((it & 1) != grp2) continue;
+            const int acc = it % kAccStages;                                    // accumulator stage of this tile ...
+            const uint32_t acc_phase = (uint32_t)(it / kAccStages) & 1u;        // ... and the parity of its current use
             if (q == 2 && lane == 0) EWVIT_TRACE(2 + grp, it, 0);
             int m_t, n_t, sp;
-            if (!decode_tile(p, w, m_t, n_t, sp)) continue;
+            if (!decode(w, m_t, n_t, sp)) continue;
 
             if ((kEpi == EPI_CONV || kEpi == EPI_BB) && n_t != cur_nt) {   // (re)stage the per-channel scale/shift of this column tile
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -773,11 +841,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         pk[2 * i] = *reinterpret_cast<const uint32_t *>(&b0);
                         pk[2 * i + 1] = *reinterpret_cast<const uint32_t *>(&b1);
                     }
-                    stage_chunk_bf16(stg, lane, pk);
+                    const uint32_t sbuf = stg + (uint32_t)(ci & 1) * kStgBytes;
+                    stage_chunk_bf16<1>(sbuf, lane, pk);
                     if (lane == 0) {
                         const int col0 = n_t * kBN + c * 32;
-                        if (p.a_mode == A_FLAT || p.a_mode == A_SCALED) tma_store_2d(&tmC, stg, p.col_off + col0, m_t * BM + q * 32);
-                        else tma_store_4d(&tmC, stg, p.col_off + col0, st_x, st_y, st_img);
+                        if (p.a_mode == A_FLAT || p.a_mode == A_SCALED) tma_store_2d(&tmC, sbuf, p.col_off + col0, m_t * BM + q * 32);
+                        else tma_store_4d(&tmC, sbuf, p.col_off + col0, st_x, st_y, st_img);
                     }
                 }
             } else
@@ -970,16 +1039,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (q == 2 && lane == 0) EWVIT_TRACE(2 + grp, it, 2);
             ewvit::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ewvit::mbar_arrive(ewvit::smem_u32(&tempty[acc]));
+            if (lane == 0) {
+                if (kPair) ewvit::mbar_arrive_leader(ewvit::smem_u32(&tempty[acc]));   // the leader's issuer waits for both CTAs' epilogues
+                else ewvit::mbar_arrive(ewvit::smem_u32(&tempty[acc]));
+            }
             if (q == 2 && lane == 0) EWVIT_TRACE(2 + grp, it, 3);
-            acc_phase ^= 1;
         }
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging buffers are read out before the CTA retires
     }
 
     ewvit::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) ewvit::tmem_dealloc(tmem_base, kTmemColsT);
+    if (kPair) ewvit::cluster_sync_all();     // the leader's MMAs read the peer's shared memory and signal its barriers until the very end
+    else __syncthreads();
+    if (warp == 1) {
+        if (kPair) ewvit::tmem_dealloc_pair(tmem_base, kTmemColsT);
+        else ewvit::tmem_dealloc(tmem_base, kTmemColsT);
+    }
 }
 
 // Split-K second pass: sum the fp32 partials, then the same epilogue as the fused path.
@@ -1028,13 +1103,13 @@ static inline int b_box_rows(int N, int bn, int tiles_n) {
 static long long *g_trace = nullptr;
 static int g_dbg = 0;
 
-template <int kEpi, bool kBuilder, int kBN, int kFast = 0>
+template <int kEpi, bool kBuilder, int kBN, int kFast = 0, bool kPair = false>
 int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, GemmParams p, cudaStream_t stream) {
     static bool attr_set[64] = {false};
     int dev = 0;
     EWVIT_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        EWVIT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kBuilder, kBN, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kEpi, kBuilder>::kSmemBytes));
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kBuilder, kBN, kFast, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kEpi, kBuilder>::kSmemBytes));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     if (p.b_tile_bytes <= 0) p.b_tile_bytes = kBN * BK * 2;
@@ -1058,6 +1133,28 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
     p.dbg = g_dbg;
     long long work = (long long)p.tiles_m * p.tiles_n * p.splits;
     long long grid = ewvit_num_sms();
+    if (kPair) {
+        // one 2-CTA cluster (= one TPC) per pair of row tiles, persistent: #clusters = min(#SMs / 2, #pair items)
+        const long long pairs = (long long)((p.tiles_m + 1) / 2) * p.tiles_n;
+        long long clusters = grid / 2;
+        if (clusters > pairs) clusters = pairs;
+        if (clusters <= 0) return EWVIT_OK;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * clusters));
+        cfg.blockDim = dim3(Cfg<kEpi, kBuilder>::kThreads);
+        cfg.dynamicSmemBytes = Cfg<kEpi, kBuilder>::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        EWVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kEpi, kBuilder, kBN, kFast, kPair>, tmA, tmB, tmC, p));
+        ewvit_count_launch();
+        return EWVIT_OK;
+    }
     if (grid > work) grid = work;
     if (grid <= 0) return EWVIT_OK;
     gemm_tc_kernel<kEpi, kBuilder, kBN, kFast><<<(unsigned)grid, Cfg<kEpi, kBuilder>::kThreads, Cfg<kEpi, kBuilder>::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
@@ -1067,6 +1164,7 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
 
 int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p, int epi, cudaStream_t stream,
                 int bn = BN) {
+    if (epi == EPI_CONV && p.pair) return launch_gemm_t<EPI_CONV, false, 128, 0, true>(tmA, tmB, tmC, p, stream);
     if (epi == EPI_CONV) return launch_gemm_t<EPI_CONV, false, 128>(tmA, tmB, tmC, p, stream);
     if (epi == EPI_BB) {
         const int fast = (g_dbg & 256) ? 0 : (p.act == 4 && !p.residual_bf16) ? 1 : p.act == 0 ? 2 : 0;
@@ -1261,10 +1359,22 @@ extern "C" int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, in
             p.flat3 = 1;
             p.num_kb = 3 * chunks;
             p.kb_per_split = p.num_kb;
-            p.stage_bytes = kFlat3ABytes + 3 * BN * BK * 2;
+            // CTA pairs (cta_group::2) whenever there are at least two row tiles: each CTA stores half of every weight tile
+            p.pair = (!(g_dbg & 128) && p.tiles_m >= 2) ? 1 : 0;
+            const int bn_rows = p.pair ? BN / 2 : BN;
+            if (p.pair) {
+                uint64_t dimsb[2] = {(uint64_t)9 * cin, (uint64_t)cout}, strb[2] = {2, (uint64_t)9 * cin * 2};
+                uint32_t boxh[2] = {BK, (uint32_t)bn_rows};
+                rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, strb, boxh, nullptr);
+                if (rc != EWVIT_OK) return rc;
+            }
+            p.b_tile_bytes = bn_rows * BK * 2;
+            p.stage_bytes = kFlat3ABytes + 3 * p.b_tile_bytes;
             p.stages = Cfg<EPI_CONV, false>::kOperandBytes / p.stage_bytes;
-            // small filter banks (the 64 -> 128 fusion conv: 144 KB) stay resident; the ring then carries activation windows only
-            const int wbytes = 9 * cin * BN * 2;
+            if (p.stages > kStages) p.stages = kStages;
+            // small filter banks (the 64 -> 128 fusion conv: 144 KB, 72 KB per CTA of a pair) stay resident; the ring then carries
+            // activation windows only
+            const int wbytes = 9 * cin * bn_rows * 2;
             if (p.tiles_n == 1 && !(g_dbg & 64) && wbytes + 3 * kFlat3ABytes <= Cfg<EPI_CONV, false>::kOperandBytes) {
                 p.b_res = 1;
                 p.stage_bytes = kFlat3ABytes;

@@ -63,6 +63,8 @@ def freeze_unused_(model, ablation):
             on_path = False                      # cls mode returns mlp_head(token 0): feat_map is never evaluated (sfe.py:163-166)
         if ablation in ("dynamic", "sfe_mwt") and (name.startswith("dama.sfe.mlp_head.") or name.startswith("sfe.mlp_head.")):
             on_path = False                      # feature-map mode never evaluates mlp_head (sfe.py:168-173)
+        if ".efficient_net._fc." in name:
+            on_path = False                      # b0's ImageNet classifier: extract_features stops before it (sfe.py:148)
         if not on_path:
             p.requires_grad_(False)
         if p.requires_grad:
