@@ -109,7 +109,10 @@ struct GemmParams {
     int a_gate_bf16;
     int a_hw;              // rows (pixels) per frame
     int a_k;               // K = row pitch of A and of the gate
-    int pair;              // flat3 convs: CTA pairs on cta_group::2 (the B tiles in shared memory hold kBN / 2 filter rows)
+    int k16;               // flat3 with 16 channels per pixel (MWT head conv): a pixel is ONE 32-byte row = one MMA K step; the window
+                           // of a vertical tap is 136 rows x 32 bytes (32B swizzle) and every (dy, dx) tap is a single MMA on it
+    int pair;              // CTA pairs on cta_group::2 (MWT flat3 convs, backbone 1x1 convs): every CTA stores b_half filter rows per B tile
+    int b_half;            // pair mode: rows of a B tile held by each CTA = half of the MMA's N
     int a_gate_smem;       // the gates of a tile's frames are staged in shared memory once per tile (bf16 gates, <= kGateFrames frames per tile)
     int flat3;           // A_FLAT 3x3 conv, "row-shared" taps: one ring slot = (dy, channel chunk) holds ONE window of
                          // kFlat3Rows activation rows and the three weight tiles of dx = 0,1,2; the three A operands are the
@@ -216,7 +219,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ewvit::tma_prefetch_desc(&tmA);
         ewvit::tma_prefetch_desc(&tmB);
         for (int s = 0; s < kStages; ++s) {
-            ewvit::mbar_init(ewvit::smem_u32(&full[s]), !kBuilder ? 1 : p.a_mode == A_SCALED ? 2 : (p.b_res ? 2 : 3));   // [TMA B] + the two warps of the slot's builder pair
+            // [TMA B] + the two warps of the slot's builder pair (A_SCALED on CTA pairs: the builder pairs of BOTH CTAs)
+            ewvit::mbar_init(ewvit::smem_u32(&full[s]), !kBuilder ? 1 : p.a_mode == A_SCALED ? (kPair ? 4 : 2) : (p.b_res ? 2 : 3));
             ewvit::mbar_init(ewvit::smem_u32(&empty[s]), 1);
         }
         for (int a = 0; a < kAccStages; ++a) {
@@ -274,16 +278,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int tt = 0;
         if (p.b_res) {     // weights are small and identical for every tile: fetch all k-blocks once
             const int nb = p.flat3 ? 3 * p.num_kb : p.num_kb;    // flat3: num_kb counts (dy, chunk) slots of three taps each
+            const int kstep = p.k16 ? 16 : BK;
             if (ewvit::elect_one()) {
                 const uint32_t bb = ewvit::smem_u32(bres_bar);
                 if (kPair) {           // each CTA keeps ITS half of the filter rows; both halves count on the leader's barrier
                     if (cta_rank == 0) ewvit::mbar_expect_tx(bb, (uint32_t)(2 * nb * kBTileB));
                     for (int kb = 0; kb < nb; ++kb)
-                        ewvit::tma_load_2d_pair(smem_base + p.bres_off + kb * kBTileB, &tmB, kb * BK, (int)cta_rank * (kBN / 2), bb);
+                        ewvit::tma_load_2d_pair(smem_base + p.bres_off + kb * kBTileB, &tmB, kb * BK, (int)cta_rank * p.b_half, bb);
                 } else {
                     ewvit::mbar_expect_tx(bb, (uint32_t)(nb * kBTileB));
                     for (int kb = 0; kb < nb; ++kb)
-                        ewvit::tma_load_2d(smem_base + p.bres_off + kb * kBTileB, &tmB, kb * BK, 0, bb);
+                        ewvit::tma_load_2d(smem_base + p.bres_off + kb * kBTileB, &tmB, kb * kstep, 0, bb);
                 }
             }
             __syncwarp();
@@ -345,7 +350,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                                 for (int dx = 0; dx < 3; ++dx)
                                     ewvit::tma_load_2d_pair(a_dst + kFlat3ABytes + dx * kBTileB, &tmB, ((dy * 3 + dx) * p.chunks_per_tap + ch) * BK,
-                                                            n_t * kBN + (int)cta_rank * (kBN / 2), bar);
+                                                            n_t * kBN + (int)cta_rank * p.b_half, bar);
                             }
                         }
                     } else if (ewvit::elect_one()) {
@@ -368,13 +373,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // A_SCALED: the builders post-process the raw tile, so completion goes to the `raw` (halo) barrier
                 const uint32_t bar = ewvit::smem_u32((kBuilder && p.a_mode == A_SCALED) ? &hfull[stage] : &full[stage]);
                 const uint32_t a_dst = smem_base + stage * kStageB;
-                if (ewvit::elect_one()) {
+                if (kPair && !(kBuilder && p.a_mode == A_SCALED)) {
+                    // plain 1x1 conv on a CTA pair: both CTAs' tiles of this slot complete on the LEADER's full barrier
+                    if (ewvit::elect_one()) {
+                        if (cta_rank == 0) ewvit::mbar_expect_tx(bar, 2 * kStageB);
+                        ewvit::tma_load_2d_pair(a_dst, &tmA, chunk * BK, m_t * BM + p.tap_a0[tap], bar);
+                        if (!p.b_res) ewvit::tma_load_2d_pair(a_dst + kTileBytes, &tmB, kb * BK, n_t * kBN + (int)cta_rank * p.b_half, bar);
+                    }
+                } else if (ewvit::elect_one()) {
+                    // (A_SCALED on a CTA pair: each CTA's raw tile + its half of B complete on its OWN raw barrier; its builders
+                    // then arrive on the leader's full barrier)
                     ewvit::mbar_expect_tx(bar, kStageB);
                     if (p.a_mode == A_FLAT || p.a_mode == A_SCALED)
                         ewvit::tma_load_2d(a_dst, &tmA, chunk * BK, m_t * BM + p.tap_a0[tap], bar);
                     else
                         ewvit::tma_load_4d(a_dst, &tmA, chunk * BK, ax0 + p.tap_a0[tap], ay0 + p.tap_a1[tap], img, bar);
-                    if (!p.b_res) ewvit::tma_load_2d(a_dst + kTileBytes, &tmB, kb * BK, n_t * kBN, bar);
+                    if (!p.b_res) ewvit::tma_load_2d(a_dst + kTileBytes, &tmB, kb * BK, n_t * kBN + (kPair ? (int)cta_rank * p.b_half : 0), bar);
                 }
                 __syncwarp();
                 if (++chunk == p.chunks_per_tap) { chunk = 0; ++tap; }
@@ -399,7 +413,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             // columns past N are zero-filled B rows: shrink the MMA's N to the valid part (multiple of 16)
             const int n_valid = min(kBN, p.N - n_t * kBN);
-            const uint32_t idesc = ewvit::umma_idesc_bf16(kPair ? 2 * BM : BM, (uint32_t)((n_valid + 15) & ~15));
+            // pair mode splits B by HALF OF THE MMA's N: with several column tiles every CTA holds kBN / 2 rows, so N stays kBN
+            // (rows past the tensor are zero-filled)
+            const uint32_t idesc = ewvit::umma_idesc_bf16(kPair ? 2 * BM : BM, (kPair && p.tiles_n > 1) ? (uint32_t)kBN : (uint32_t)((n_valid + 15) & ~15));
             ewvit::mbar_wait(ewvit::smem_u32(&tempty[acc]), acc_phase ^ 1);
             ewvit::tc_fence_after();
             if (lane == 0) EWVIT_TRACE(1, tt, 1);
@@ -413,7 +429,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint64_t b_desc = ewvit::umma_desc_sw128(p.b_res ? smem_base + p.bres_off + kb * kBTileB : a_addr + kTileBytes);
                 const uint32_t ebar = ewvit::smem_u32(&empty[stage]);
                 const uint32_t first = kb > kb0 ? 1u : 0u;
-                if (p.flat3) {
+                if (p.flat3 && p.k16) {
+                    // 16 channels per pixel: tap (dy = kb, dx) is ONE K = 16 MMA on the window shifted by dx rows of 32 bytes
+                    if (ewvit::elect_one()) {
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx)
+                            ewvit::umma_bf16(d_tmem, ewvit::umma_desc_sw32(a_addr + dx * 32),
+                                             ewvit::umma_desc_sw32(smem_base + p.bres_off + (kb * 3 + dx) * kBTileB), idesc, (dx > 0 || kb > kb0) ? 1u : 0u);
+                        ewvit::umma_commit(ebar);
+                    }
+                } else if (p.flat3) {
                     if (ewvit::elect_one()) {
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx) {
@@ -441,11 +466,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 } else if (ewvit::elect_one()) {
                     // advancing 16 K-elements = 32 bytes = +2 in the descriptor's (address >> 4) field
-                    ewvit::umma_bf16(d_tmem, a_desc, b_desc, idesc, first);
-                    ewvit::umma_bf16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
-                    ewvit::umma_bf16(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
-                    ewvit::umma_bf16(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
-                    ewvit::umma_commit(ebar);   // frees the smem slot when the MMAs retire
+                    if (kPair) {
+                        ewvit::umma_bf16_pair(d_tmem, a_desc, b_desc, idesc, first);
+                        ewvit::umma_bf16_pair(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                        ewvit::umma_bf16_pair(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                        ewvit::umma_bf16_pair(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                        ewvit::umma_commit_pair(ebar);
+                    } else {
+                        ewvit::umma_bf16(d_tmem, a_desc, b_desc, idesc, first);
+                        ewvit::umma_bf16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                        ewvit::umma_bf16(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                        ewvit::umma_bf16(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                        ewvit::umma_commit(ebar);   // frees the smem slot when the MMAs retire
+                    }
                 }
                 __syncwarp();
                 if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -489,21 +522,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int kchunks = p.a_k >> 3;                       // 16-byte chunks per gate row
             uint4 gpre[kGateChunks];
             auto gate_prefetch = [&](int w2) {
-                const int f0n = (int)(((long long)(w2 % p.tiles_m) * BM) / p.a_hw);
+                int m2 = 0, n2 = 0, s2 = 0;
+                if (w2 < w_total) decode(w2, m2, n2, s2);
+                const int f0n = (int)(((long long)m2 * BM) / p.a_hw);
 #pragma unroll
                 for (int q = 0; q < kGateChunks; ++q) {
                     const int ch = btid + q * (32 * kBuilderWarps);
                     const int fr = ch / kchunks, cc = ch - fr * kchunks;
                     gpre[q] = make_uint4(0u, 0u, 0u, 0u);
-                    if (fr < kGateFrames && w2 < total_work)
+                    if (fr < kGateFrames && w2 < w_total)
                         gpre[q] = __ldg(reinterpret_cast<const uint4 *>(static_cast<const __nv_bfloat16 *>(p.a_gate) +
                                                                         (long long)min(f0n + fr, last_frame) * p.a_k) + cc);
                 }
             };
-            if (gsm) gate_prefetch(blockIdx.x);
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const int m_t = w % p.tiles_m;
-                const int sp = (w / p.tiles_m) / p.tiles_n;
+            if (gsm) gate_prefetch(w_first);
+            for (int w = w_first; w < w_total; w += w_step) {
+                int m_t, n_t_unused, sp;
+                decode(w, m_t, n_t_unused, sp);
                 const int kb0 = sp * p.kb_per_split;
                 const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
                 // gate row (frame) of each of this thread's 16 tile rows; rows past M are zero-filled by TMA
@@ -531,7 +566,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                          "r"(gpre[q].z), "r"(gpre[q].w) : "memory");
                     }
                     asm volatile("bar.sync 3, %0;" ::"n"(32 * kBuilderWarps) : "memory");
-                    gate_prefetch(w + gridDim.x);
+                    gate_prefetch(w + w_step);
                 }
                 for (int kb = kb0; kb < kb1; ++kb, ++g) {
                     const int stage = (int)(g % (uint32_t)nstages);
@@ -642,7 +677,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     ewvit::fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
                     __syncwarp();
-                    if (lane == 0) ewvit::mbar_arrive(ewvit::smem_u32(&full[stage]));
+                    if (lane == 0) {
+                        if (kPair) ewvit::mbar_arrive_leader(ewvit::smem_u32(&full[stage]));   // the issuer waits for the builders of both CTAs
+                        else ewvit::mbar_arrive(ewvit::smem_u32(&full[stage]));
+                    }
                 }
             }
         } else {
@@ -1169,12 +1207,16 @@ int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMa
     if (epi == EPI_BB) {
         const int fast = (g_dbg & 256) ? 0 : (p.act == 4 && !p.residual_bf16) ? 1 : p.act == 0 ? 2 : 0;
         const bool builder = p.a_mode == A_IM2COL || p.a_mode == A_SCALED;
-#define EWVIT_BB(B_, N_)                                                                              \
-        (fast == 1 ? launch_gemm_t<EPI_BB, B_, N_, 1>(tmA, tmB, tmC, p, stream)                           \
-         : fast == 2 ? launch_gemm_t<EPI_BB, B_, N_, 2>(tmA, tmB, tmC, p, stream)                         \
-                     : launch_gemm_t<EPI_BB, B_, N_, 0>(tmA, tmB, tmC, p, stream))
-        if (builder) return bn == 256 ? EWVIT_BB(true, 256) : EWVIT_BB(true, 128);
-        return bn == 256 ? EWVIT_BB(false, 256) : EWVIT_BB(false, 128);
+#define EWVIT_BB(B_, N_, P_)                                                                          \
+        (fast == 1 ? launch_gemm_t<EPI_BB, B_, N_, 1, P_>(tmA, tmB, tmC, p, stream)                       \
+         : fast == 2 ? launch_gemm_t<EPI_BB, B_, N_, 2, P_>(tmA, tmB, tmC, p, stream)                     \
+                     : launch_gemm_t<EPI_BB, B_, N_, 0, P_>(tmA, tmB, tmC, p, stream))
+        if (p.pair) {        // 1x1 convs on CTA pairs (A_FLAT plain, A_SCALED gated)
+            if (builder) return bn == 256 ? EWVIT_BB(true, 256, true) : EWVIT_BB(true, 128, true);
+            return bn == 256 ? EWVIT_BB(false, 256, true) : EWVIT_BB(false, 128, true);
+        }
+        if (builder) return bn == 256 ? EWVIT_BB(true, 256, false) : EWVIT_BB(true, 128, false);
+        return bn == 256 ? EWVIT_BB(false, 256, false) : EWVIT_BB(false, 128, false);
 #undef EWVIT_BB
     }
     if (epi == EPI_PARTIAL) return launch_gemm_t<EPI_PARTIAL, false, 128>(tmA, tmB, tmC, p, stream);
@@ -1198,7 +1240,7 @@ ewvit_encode_tiled_fn ewvit_get_encode_tiled() {
 }
 
 int ewvit_make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t *dims,
-                         const uint64_t *strides_bytes, const uint32_t *box, const uint32_t *estr, bool swizzle128) {
+                         const uint64_t *strides_bytes, const uint32_t *box, const uint32_t *estr, bool swizzle128, bool swizzle32) {
     ewvit_encode_tiled_fn enc = ewvit_get_encode_tiled();
     EWVIT_REQUIRE(enc != nullptr, EWVIT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[5], gstr[5];
@@ -1210,7 +1252,8 @@ int ewvit_make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uin
     }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i + 1];
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bdim,
-                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     EWVIT_REQUIRE(r == CUDA_SUCCESS, EWVIT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
@@ -1368,6 +1411,7 @@ extern "C" int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, in
                 rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, strb, boxh, nullptr);
                 if (rc != EWVIT_OK) return rc;
             }
+            p.b_half = bn_rows;
             p.b_tile_bytes = bn_rows * BK * 2;
             p.stage_bytes = kFlat3ABytes + 3 * p.b_tile_bytes;
             p.stages = Cfg<EPI_CONV, false>::kOperandBytes / p.stage_bytes;
@@ -1505,6 +1549,16 @@ static int conv_nhwc_impl(const void *x, const void *w, int n, int h, int wd, in
         p.kb_per_split = num_kb;
         p.M = rows;
         p.tiles_m = (int)((rows + BM - 1) / BM);
+        if (!(g_dbg & 128) && p.tiles_m >= 2) {
+            // CTA pairs: each CTA stores half of every weight tile (half of the MMA's N: kBN / 2 rows with several column tiles,
+            // else half of the 16-aligned channel count) -- a ring slot shrinks by a third and so do the L2 -> shared bytes
+            p.pair = 1;
+            p.b_half = (p.tiles_n > 1 ? bn : brows) / 2;
+            uint32_t boxh[2] = {BK, (uint32_t)p.b_half};
+            rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, str, boxh, nullptr);
+            if (rc != EWVIT_OK) return rc;
+            p.b_tile_bytes = p.b_half * BK * 2;
+        }
     } else {
         EWVIT_REQUIRE(cin <= BK || cin % BK == 0, EWVIT_ERR_UNSUPPORTED,
                       "ewvit_conv_nhwc_bf16: 3x3 needs cin <= 64 or cin %% 64 == 0 (got %d)", cin);
@@ -1600,11 +1654,11 @@ extern "C" int ewvit_conv_nhwc_bf16_ex(const void *x, const void *w, int n, int 
 
 // Tensor-core head of one wavelet level, step 2 (mwt.py:84-86): the three per-colour Conv2d(3->18, 3x3, p1)+BN+ReLU as
 // ONE block-diagonal 9(16) -> 54(64) conv.  The input is the padded-flat [n, h+2, wd+2, 16] bf16 tensor of
-// ewvit_mwt_upsample_fwd.  With 16 channels per pixel, the three horizontal taps of an output pixel are 48 CONTIGUOUS
-// elements of that tensor, so the im2col row of a vertical tap dy is an overlapping window: the A operand comes from a
-// tensor map whose rows are 48 elements long but only 16 elements (one pixel) apart, fetched as 64-wide boxes whose last
-// 16 columns lie outside the map and are zero-filled.  K = 3 x 64, no im2col buffer, no builder warps.
-//   w [64, 192] bf16: w[g*18+oc][dy*64 + dx*16 + g*3+ic] = seperate[g].weight[oc][ic][dy][dx], zero elsewhere
+// ewvit_mwt_upsample_fwd.  With 16 channels per pixel a pixel is exactly one 32-byte row = one MMA K step, so the conv is nine
+// K = 16 MMAs per 128-pixel tile: per vertical tap ONE window of 136 pixel rows (4.3 KB, 32B-swizzled) is fetched and its three
+// horizontal taps read it at start addresses shifted by 0 / 32 / 64 bytes.  (Round 1 fetched three overlapping 64-wide windows
+// per tile, 48 KB: the kernel was bound by L2 -> shared-memory traffic at ~13 TB/s; now 13 KB per tile and the output write bounds it.)
+//   w [64, 144] bf16: w[g*18+oc][(dy*3 + dx)*16 + g*3+ic] = seperate[g].weight[oc][ic][dy][dx], zero elsewhere
 //   scale/shift [64] fp32 (folded BN, zeros past 54);  y [n, h+2, wd+2, 64] bf16 padded-flat (border written as zeros)
 extern "C" int ewvit_mwt_head_conv_fwd(const void *up, const void *w, int n, int h, int wd, const float *scale, const float *shift,
                                        void *y, void *stream) {
@@ -1619,6 +1673,8 @@ extern "C" int ewvit_mwt_head_conv_fwd(const void *up, const void *w, int n, int
     const long long rows = (long long)n * hin * win;
     GemmParams p = {};
     p.a_mode = A_FLAT;
+    p.flat3 = 1;                  // one ring slot per vertical tap: a window of 136 pixel rows shared by its three horizontal taps
+    p.k16 = 1;                    // ... of 32 bytes each (16 channels = one MMA K step), 32B-swizzled
     p.chunks_per_tap = 1;
     p.num_kb = 3;
     p.kb_per_split = 3;
@@ -1627,24 +1683,28 @@ extern "C" int ewvit_mwt_head_conv_fwd(const void *up, const void *w, int n, int
     p.tiles_n = 1;
     p.M = rows;
     p.tiles_m = (int)((rows + BM - 1) / BM);
-    for (int dy = 0; dy < 3; ++dy) p.tap_a0[dy] = (dy - 1) * win - 1;     // window starts at the left neighbour
+    for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx) p.tap_a0[dy * 3 + dx] = (dy - 1) * win + (dx - 1);
     p.pad_hp = hin;
     p.pad_wp = win;
     p.out = y; p.out_fp32 = 0; p.ldo = cout; p.col_off = 0;
     p.scale = scale; p.shift = shift; p.act = 1;
     CUtensorMap tmA, tmB, tmC;
     {
-        // overlapping rows: row i = elements [16 i, 16 i + 48) of the flat tensor
-        uint64_t dims[2] = {(uint64_t)3 * cpx, (uint64_t)(rows - 2)}, str[2] = {2, (uint64_t)cpx * 2};
-        uint32_t box[2] = {BK, BM};
-        rc = ewvit_make_tmap_bf16(&tmA, up, 2, dims, str, box, nullptr);
+        uint64_t dims[2] = {(uint64_t)cpx, (uint64_t)rows}, str[2] = {2, (uint64_t)cpx * 2};
+        uint32_t box[2] = {(uint32_t)cpx, (uint32_t)kFlat3Rows};
+        rc = ewvit_make_tmap_bf16(&tmA, up, 2, dims, str, box, nullptr, false, /*swizzle32=*/true);
         if (rc != EWVIT_OK) return rc;
-        uint64_t dimsb[2] = {(uint64_t)3 * BK, (uint64_t)cout}, strb[2] = {2, (uint64_t)3 * BK * 2};
-        uint32_t boxb[2] = {BK, (uint32_t)cout};
-        p.b_tile_bytes = cout * BK * 2;
-        rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, strb, boxb, nullptr);
+        uint64_t dimsb[2] = {(uint64_t)9 * cpx, (uint64_t)cout}, strb[2] = {2, (uint64_t)9 * cpx * 2};
+        uint32_t boxb[2] = {(uint32_t)cpx, (uint32_t)cout};
+        rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, strb, boxb, nullptr, false, /*swizzle32=*/true);
         if (rc != EWVIT_OK) return rc;
     }
+    p.b_tile_bytes = cout * cpx * 2;                     // 2 KB per (dy, dx) tap
+    p.stage_bytes = kFlat3Rows * cpx * 2;                // 4352 bytes = 17 swizzle atoms of 256 bytes
+    p.b_res = 1;                                         // all nine weight tiles (18 KB) stay resident
+    p.stages = kStages;
+    p.bres_off = p.stages * p.stage_bytes;
     rc = make_out_tmap(&tmC, y, true, rows, cout, 0, 0, 0);
     if (rc != EWVIT_OK) return rc;
     return launch_gemm(tmA, tmB, tmC, p, EPI_CONV, (cudaStream_t)stream);
@@ -1700,11 +1760,16 @@ extern "C" int ewvit_conv1x1_gated_nhwc_bf16(const void *x, const void *gate, in
     p.shift = bias; p.act = act;
     p.residual_bf16 = static_cast<const __nv_bfloat16 *>(residual);
     p.ldr = cout;
-    const int brows = b_box_rows(cout, bn, p.tiles_n);
+    int brows = b_box_rows(cout, bn, p.tiles_n);
+    if (!(g_dbg & 128) && p.tiles_m >= 2) {      // CTA pairs: half of every weight tile per CTA
+        p.pair = 1;
+        p.b_half = (p.tiles_n > 1 ? bn : brows) / 2;
+        brows = p.b_half;
+    }
     p.b_tile_bytes = brows * BK * 2;
     p.stage_bytes = kTileBytes + p.b_tile_bytes;
     p.stages = Cfg<EPI_BB, true>::kOperandBytes / p.stage_bytes;
-    if (p.stages > 6) p.stages = 6;
+    if (p.stages > 8) p.stages = 8;
     CUtensorMap tmA, tmB, tmC;
     uint64_t dimsa[2] = {(uint64_t)cin, (uint64_t)rows}, dimsb[2] = {(uint64_t)cin, (uint64_t)cout}, str[2] = {2, (uint64_t)cin * 2};
     uint32_t boxa[2] = {BK, BM}, boxb[2] = {BK, (uint32_t)brows};

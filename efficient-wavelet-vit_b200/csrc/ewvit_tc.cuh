@@ -15,7 +15,8 @@ ewvit_encode_tiled_fn ewvit_get_encode_tiled();
 // bf16 tensor, `rank` dims (innermost first), 128-byte swizzle, zero OOB fill.
 // dims[i] elements, strides_bytes[i] for i>=1 (stride of dim 0 is the element size), box[i], estr[i].
 int ewvit_make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t *dims,
-                         const uint64_t *strides_bytes, const uint32_t *box, const uint32_t *estr, bool swizzle128 = true);
+                         const uint64_t *strides_bytes, const uint32_t *box, const uint32_t *estr, bool swizzle128 = true,
+                         bool swizzle32 = false);
 
 #ifdef __CUDACC__
 namespace ewvit {
@@ -46,6 +47,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)(base_offset & 7u) << 49;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Same for rows of 32 bytes (16 bf16 = ONE MMA K step), 32B swizzle: 8-row groups are 256 bytes apart, layout type 6.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(256u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
     return d;
 }
 

@@ -127,12 +127,12 @@ class MwtRunner:
         self.head_w = torch.stack([sd[f"hf_conv.seperate.{i}.0.weight"].float() for i in range(3)]).contiguous()
         sc, sh = zip(*[_fold_bn(sd, f"hf_conv.seperate.{i}.0.", f"hf_conv.seperate.{i}.1.") for i in range(3)])
         self.head_scale, self.head_shift = torch.cat(sc).contiguous(), torch.cat(sh).contiguous()
-        # tensor-core head: the three convs as one block-diagonal [64, 3 x 64] bf16 matrix, k = dy*64 + dx*16 + (3g + ic)
-        wbd = torch.zeros((64, 3, 4, 16), dtype=torch.float32, device=dev)
+        # tensor-core head: the three convs as one block-diagonal [64, 9 x 16] bf16 matrix, k = (dy*3 + dx)*16 + (3g + ic)
+        wbd = torch.zeros((64, 3, 3, 16), dtype=torch.float32, device=dev)
         for g in range(3):
             wg = self.head_w[g]                                   # [18, 3, ky, kx]
-            wbd[g * 18:(g + 1) * 18, :, :3, g * 3:(g + 1) * 3] = wg.permute(0, 2, 3, 1)
-        self.head_wbd = wbd.reshape(64, 192).to(torch.bfloat16).contiguous()
+            wbd[g * 18:(g + 1) * 18, :, :, g * 3:(g + 1) * 3] = wg.permute(0, 2, 3, 1)
+        self.head_wbd = wbd.reshape(64, 144).to(torch.bfloat16).contiguous()
         self.head_scale64 = torch.zeros(64, dtype=torch.float32, device=dev)
         self.head_shift64 = torch.zeros(64, dtype=torch.float32, device=dev)
         self.head_scale64[:54] = self.head_scale

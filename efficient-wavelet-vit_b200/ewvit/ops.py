@@ -196,14 +196,14 @@ def mwt_upsample(hf, up, hout, wout):
 
 
 def mwt_head_conv(up, w, scale, shift, y, h, wd):
-    """up [n,h+2,wd+2,16] bf16, w [64,192] bf16, scale/shift [64] fp32 -> y [n,h+2,wd+2,64] bf16 (see include/ewvit.h)."""
+    """up [n,h+2,wd+2,16] bf16, w [64,144] bf16, scale/shift [64] fp32 -> y [n,h+2,wd+2,64] bf16 (see include/ewvit.h)."""
     _check_bf16(up, "up")
     _check_bf16(w, "w", 2)
     _check_bf16(y, "y")
     _check_f32(scale, "scale")
     _check_f32(shift, "shift")
     n = up.numel() // ((h + 2) * (wd + 2) * 16)
-    if up.numel() != n * (h + 2) * (wd + 2) * 16 or y.numel() != n * (h + 2) * (wd + 2) * 64 or tuple(w.shape) != (64, 192) \
+    if up.numel() != n * (h + 2) * (wd + 2) * 16 or y.numel() != n * (h + 2) * (wd + 2) * 64 or tuple(w.shape) != (64, 144) \
             or scale.numel() != 64 or shift.numel() != 64:
         raise EwvitError("mwt_head_conv: shape mismatch")
     with torch.cuda.device(up.device):

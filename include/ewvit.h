@@ -158,7 +158,7 @@ EWVIT_API int ewvit_mwt_head_mma_fwd(const float *hf, int n, int hin, int win, i
  *      up [n, hout+2, wout+2, 16] bf16 padded-flat NHWC (channels 9..15 zero).  Only interior pixels are written: the
  *      one-pixel border must be zero (zero the buffer once).
  *   2. ewvit_mwt_head_conv_fwd: the three Conv2d(3->18,3x3,p1)+BN+ReLU as one block-diagonal conv on the tensor cores.
- *      w [64, 192] bf16 with w[g*18+oc][dy*64 + dx*16 + g*3+ic] = seperate[g].weight[oc][ic][dy][dx] (zero elsewhere),
+ *      w [64, 144] bf16 with w[g*18+oc][(dy*3 + dx)*16 + g*3+ic] = seperate[g].weight[oc][ic][dy][dx] (zero elsewhere),
  *      scale/shift [64] fp32 (folded bias + eval BatchNorm, zeros past channel 54),
  *      y [n, h+2, wd+2, 64] bf16 padded-flat NHWC (channels 54..63 and the border come out as zeros). */
 EWVIT_API int ewvit_mwt_upsample_fwd(const float *hf, int n, int hin, int win, int hout, int wout, void *up, void *stream);
