@@ -824,7 +824,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 valid = orow < p.M;
                 if (p.pad_hp > 0) {
                     const long long img_rows = (long long)p.pad_hp * p.pad_wp;
-                    const int qi = (int)(orow % img_rows);
+                    // 32-bit arithmetic whenever the row index fits (a 64-bit modulo is ~10x the cost and this runs per tile)
+                    const int qi = orow < 0x7fffffffLL ? (int)((unsigned)orow % (unsigned)img_rows) : (int)(orow % img_rows);
                     const int y = qi / p.pad_wp, x = qi - y * p.pad_wp;
                     zero = (y == 0) || (y == p.pad_hp - 1) || (x == 0) || (x == p.pad_wp - 1);
                 }
@@ -1656,8 +1657,10 @@ extern "C" int ewvit_conv_nhwc_bf16_ex(const void *x, const void *w, int n, int 
 // ONE block-diagonal 9(16) -> 54(64) conv.  The input is the padded-flat [n, h+2, wd+2, 16] bf16 tensor of
 // ewvit_mwt_upsample_fwd.  With 16 channels per pixel a pixel is exactly one 32-byte row = one MMA K step, so the conv is nine
 // K = 16 MMAs per 128-pixel tile: per vertical tap ONE window of 136 pixel rows (4.3 KB, 32B-swizzled) is fetched and its three
-// horizontal taps read it at start addresses shifted by 0 / 32 / 64 bytes.  (Round 1 fetched three overlapping 64-wide windows
-// per tile, 48 KB: the kernel was bound by L2 -> shared-memory traffic at ~13 TB/s; now 13 KB per tile and the output write bounds it.)
+// horizontal taps read it at start addresses shifted by 0 / 32 / 64 bytes: 13 KB per tile instead of the 48 KB of three
+// overlapping 64-wide windows.  Measured: the kernel time did NOT change (0.19 ms per 256 frames either way) -- a tiled TMA load
+// costs ~3 cycles per box ROW whatever the row length (408 rows per tile in both layouts), and with the loads replaced by
+// cp.async copies (tried, dropped) the per-tile cost of the epilogue (~2400 cycles per 128 x 64 tile and group) is next in line.
 //   w [64, 144] bf16: w[g*18+oc][(dy*3 + dx)*16 + g*3+ic] = seperate[g].weight[oc][ic][dy][dx], zero elsewhere
 //   scale/shift [64] fp32 (folded BN, zeros past 54);  y [n, h+2, wd+2, 64] bf16 padded-flat (border written as zeros)
 extern "C" int ewvit_mwt_head_conv_fwd(const void *up, const void *w, int n, int h, int wd, const float *scale, const float *shift,

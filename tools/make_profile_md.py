@@ -13,8 +13,11 @@ import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
-OUT = os.path.join(REPO, "profiles")
-GO = os.path.join(REPO, "gpurun_out")
+# optional: directory holding launches_<tag>.csv / prof_<tag>_*.ncu-rep and directory to write the summaries to (on the GPU box the
+# reports stay in /tmp -- they are tens of MB each -- and only the summaries travel back through gpurun_out/)
+GO = sys.argv[2] if len(sys.argv) > 2 else os.path.join(REPO, "gpurun_out")
+OUT = sys.argv[3] if len(sys.argv) > 3 else os.path.join(REPO, "profiles")
+os.makedirs(OUT, exist_ok=True)
 
 COLS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
