@@ -547,25 +547,6 @@ __global__ void __launch_bounds__(kSeThreads) se_gate_kernel(const float *__rest
     }
 }
 
-// ---- x[n, hw, c] *= gate[n, c] in place, 8 channels (16 bytes) per thread
-__global__ void __launch_bounds__(256) se_scale_kernel(__nv_bfloat16 *__restrict__ x, const float *__restrict__ gate,
-                                                       long long total8, int hw, int c8) {
-    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total8; i += (long long)gridDim.x * 256) {
-        const int cg = (int)(i % c8);
-        const long long img = i / ((long long)hw * c8);
-        uint4 v = *reinterpret_cast<uint4 *>(x + i * 8);
-        const float4 g0 = *reinterpret_cast<const float4 *>(gate + (img * c8 + cg) * 8);
-        const float4 g1 = *reinterpret_cast<const float4 *>(gate + (img * c8 + cg) * 8 + 4);
-        __nv_bfloat162 *vp = reinterpret_cast<__nv_bfloat162 *>(&v);
-        float2 f;
-        f = __bfloat1622float2(vp[0]); vp[0] = __floats2bfloat162_rn(f.x * g0.x, f.y * g0.y);
-        f = __bfloat1622float2(vp[1]); vp[1] = __floats2bfloat162_rn(f.x * g0.z, f.y * g0.w);
-        f = __bfloat1622float2(vp[2]); vp[2] = __floats2bfloat162_rn(f.x * g1.x, f.y * g1.y);
-        f = __bfloat1622float2(vp[3]); vp[3] = __floats2bfloat162_rn(f.x * g1.z, f.y * g1.w);
-        *reinterpret_cast<uint4 *>(x + i * 8) = v;
-    }
-}
-
 }  // namespace
 
 static int stem_impl(const void *x, bool u8, const float *mean, const float *stdv, int n, int h, int wd, const float *w, const float *bias,
@@ -697,35 +678,6 @@ extern "C" int ewvit_conv3x3_c24_fwd(const void *x, const void *w, int wk, const
     conv3x3_c24_kernel<<<(unsigned)grid, 256, kC24Smem, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16 *>(x),
                                                                                static_cast<const __nv_bfloat16 *>(w), wk, bias,
                                                                                static_cast<__nv_bfloat16 *>(y), n, h, wd, residual ? 1 : 0);
-    EWVIT_LAUNCH_OK();
-    return EWVIT_OK;
-}
-
-extern "C" int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const float *w1, const float *b1, const float *w2t,
-                                        const float *b2, int n, int hw, int c, int sq, float *gate_ws, void *stream) {
-    EWVIT_REQUIRE(n >= 0 && hw > 0 && c > 0 && sq > 0, EWVIT_ERR_INVALID_ARG, "ewvit_se_apply_nhwc_bf16: bad sizes");
-    if (n == 0) return EWVIT_OK;
-    EWVIT_REQUIRE(x && pooled && w1 && b1 && w2t && b2 && gate_ws && ewvit_aligned16(x) && ewvit_aligned16(gate_ws) &&
-                      ewvit_aligned16(pooled) && ewvit_aligned16(w1) && ewvit_aligned16(w2t) && ewvit_aligned16(b2), EWVIT_ERR_INVALID_ARG,
-                  "ewvit_se_apply_nhwc_bf16: NULL or misaligned pointer");
-    const size_t gate_smem = (size_t)kSeF * (c + sq) * sizeof(float);
-    EWVIT_REQUIRE(c % 8 == 0 && c <= kSeMaxC && gate_smem <= 160 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_se_apply_nhwc_bf16: c=%d sq=%d not supported", c, sq);
-    int rc = ewvit_check_device();
-    if (rc != EWVIT_OK) return rc;
-    static bool se_attr[64] = {false};
-    int dev = 0;
-    EWVIT_CUDA_OK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !se_attr[dev]) {
-        EWVIT_CUDA_OK(cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        if (dev >= 0 && dev < 64) se_attr[dev] = true;
-    }
-    se_gate_kernel<<<(unsigned)((n + kSeF - 1) / kSeF), kSeThreads, gate_smem, (cudaStream_t)stream>>>(pooled, w1, b1, w2t, b2, gate_ws, n, c, sq, 0, 1);
-    EWVIT_LAUNCH_OK();
-    const long long total8 = (long long)n * hw * (c / 8);
-    long long blocks = (total8 + 255) / 256;
-    const long long cap = (long long)ewvit_num_sms() * 16;
-    if (blocks > cap) blocks = cap;
-    se_scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(static_cast<__nv_bfloat16 *>(x), gate_ws, total8, hw, c / 8);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }

@@ -30,7 +30,6 @@ SIGNATURES = {
                                   c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "ewvit_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "ewvit_mwt_head_fwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "ewvit_maxpool2x2_nhwc_bf16": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
     "ewvit_gap_nhwc_bf16": (c_int, [P, c_int64, c_int, c_int, P, c_int64, P]),
     "ewvit_vit_assemble": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, P]),
@@ -47,12 +46,10 @@ SIGNATURES = {
     "ewvit_stem_conv_same_fwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P]),
     "ewvit_conv_nhwc_bf16_ex": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, c_int, c_int, P]),
     "ewvit_dwconv3x3_nhwc_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
-    "ewvit_se_apply_nhwc_bf16": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     "ewvit_se_gate_fwd": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, P, c_int, P]),
     "ewvit_dwconv_nhwc_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "ewvit_dwconv_pool_parts": (c_int, [c_int, c_int, c_int, c_int]),
     "ewvit_conv1x1_gated_nhwc_bf16": (c_int, [P, P, c_int, P, c_int, c_int, c_int, c_int, P, c_int, P, P, P]),
-    "ewvit_mwt_head_mma_fwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "ewvit_mwt_upsample_fwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "ewvit_mwt_head_conv_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P]),
     "ewvit_binary_metrics_fwd": (c_int, [P, P, c_int, P, P]),

@@ -165,24 +165,6 @@ def _check_f32(t, name):
         raise EwvitError(f"{name} must be a contiguous fp32 CUDA tensor")
 
 
-def mwt_head(hf, w, scale, shift, y, hout, wout, mma=False):
-    """hf [n,9,hin,win] fp32 -> y [n,hout+2,wout+2,64] bf16 (interior written). See include/ewvit.h.
-    mma=True: the warp-level tensor-core kernel (bf16 operands), else the fp32 CUDA-core kernel."""
-    for t, nm in ((hf, "hf"), (w, "w"), (scale, "scale"), (shift, "shift")):
-        _check_f32(t, nm)
-    _check_bf16(y, "y")
-    n, c9, hin, win = hf.shape
-    if c9 != 9 or w.numel() != 3 * 18 * 27 or scale.numel() != 54 or shift.numel() != 54:
-        raise EwvitError("mwt_head: expects 9 high-frequency channels (in_channels=3) and 3x18x27 weights")
-    if y.numel() != n * (hout + 2) * (wout + 2) * 64:
-        raise EwvitError("mwt_head: bad y size")
-    fn = load().ewvit_mwt_head_mma_fwd if mma else load().ewvit_mwt_head_fwd
-    with torch.cuda.device(hf.device):
-        check(fn(hf.data_ptr(), n, hin, win, hout, wout, w.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), _stream()),
-              "ewvit_mwt_head_mma_fwd" if mma else "ewvit_mwt_head_fwd")
-    return y
-
-
 def mwt_upsample(hf, up, hout, wout):
     """hf [n,9,hin,win] fp32 -> up [n,hout+2,wout+2,16] bf16 (interior written, channels 9..15 zero)."""
     _check_f32(hf, "hf")
@@ -440,22 +422,6 @@ def dwconv3x3(x, w9c, bias, stride, out=None, pooled=None):
         check(load().ewvit_dwconv3x3_nhwc_bf16(x.data_ptr(), w9c.data_ptr(), bias.data_ptr(), n, h, wd, c, stride,
                                                out.data_ptr(), _ptr(pooled), _stream()), "ewvit_dwconv3x3_nhwc_bf16")
     return out
-
-
-def se_apply(x, pooled, w1, b1, w2t, b2, gate_ws=None):
-    """In-place squeeze-excitation scaling of NHWC bf16 x [n,h,w,c] from pooled [n,c]."""
-    _check_bf16(x, "x", 4)
-    n, h, wd, c = x.shape
-    sq = w1.shape[0]
-    for t, nm in ((pooled, "pooled"), (w1, "w1"), (b1, "b1"), (w2t, "w2t"), (b2, "b2")):
-        _check_f32(t, nm)
-    if gate_ws is None:
-        gate_ws = torch.empty((n, c), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
-        check(load().ewvit_se_apply_nhwc_bf16(x.data_ptr(), pooled.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2t.data_ptr(),
-                                              b2.data_ptr(), n, h * wd, c, sq, gate_ws.data_ptr(), _stream()),
-              "ewvit_se_apply_nhwc_bf16")
-    return x
 
 
 def se_gate(pooled, w1, b1, w2t, b2, out=None, bf16=False):

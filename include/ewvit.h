@@ -134,26 +134,9 @@ EWVIT_API int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, int
  * MWT glue  (rows a-3, a-4)
  * ------------------------------------------------------------------------------------------- */
 
-/* High-frequency head of one wavelet level: reference network/mwt.py:77-86 --
- * `hf[0].reshape(B, 3C, h, w)` (colour-major), `F.interpolate(..., mode='bilinear')` to the level-1 grid
- * (align_corners=False; identity when hin == hout), then the three per-colour Conv2d(3->18,3x3,p1)+BN+ReLU
- * of hf_conv['seperate'] and their channel concat.
- *   hf    [n, 9, hin, win] fp32   (= yh of ewvit_dwt*_haar_fwd viewed as [n, 3*3, hin, win])
- *   w     [3, 18, 3, 3, 3] fp32   (group, out channel, in channel, ky, kx) = the three conv weights stacked
- *   scale [54], shift [54] fp32   folded conv bias + eval BatchNorm per concatenated channel
- *   y     [n, hout+2, wout+2, 64] bf16 padded-flat NHWC; only the interior pixels are written (channels 54..63
- *         as zeros); the one-pixel border must be zero (zero the buffer once). */
-EWVIT_API int ewvit_mwt_head_fwd(const float *hf, int n, int hin, int win, int hout, int wout, const float *w,
-                                 const float *scale, const float *shift, void *y, void *stream);
-
-/* The same head (network/mwt.py:77-86) as ONE kernel on warp-level tensor-core MMAs: the bilinear upsample is evaluated
- * straight into a shared-memory halo and the block-diagonal 9 -> 54 conv runs as a direct convolution (ldmatrix on
- * tap-shifted halo pixels, mma.sync.m16n8k16), so the 16-channel intermediate never exists in HBM.  Same arguments and
- * output contract as ewvit_mwt_head_fwd (operands rounded to bf16, fp32 accumulation). */
-EWVIT_API int ewvit_mwt_head_mma_fwd(const float *hf, int n, int hin, int win, int hout, int wout, const float *w,
-                                     const float *scale, const float *shift, void *y, void *stream);
-
-/* Tensor-core variant of the high-frequency head (same reference lines, network/mwt.py:77-86), in two steps:
+/* High-frequency head of one wavelet level: reference network/mwt.py:77-86 -- `hf[0].reshape(B, 3C, h, w)` (colour-major),
+ * `F.interpolate(..., mode='bilinear')` to the level-1 grid (align_corners=False; identity when hin == hout), then the three
+ * per-colour Conv2d(3->18,3x3,p1)+BN+ReLU of hf_conv['seperate'] and their channel concat -- in two steps:
  *   1. ewvit_mwt_upsample_fwd: hf [n, 9, hin, win] fp32 -> bilinear upsample (identity when hin == hout) ->
  *      up [n, hout+2, wout+2, 16] bf16 padded-flat NHWC (channels 9..15 zero).  Only interior pixels are written: the
  *      one-pixel border must be zero (zero the buffer once).
@@ -290,14 +273,9 @@ EWVIT_API int ewvit_dwconv_nhwc_bf16(const void *x, const float *w, const float 
                                      void *stream);
 EWVIT_API int ewvit_dwconv_pool_parts(int ho, int wo, int ksize, int stride);
 
-/* Squeeze-excitation (torchvision.ops.SqueezeExcitation with SiLU / Sigmoid): gate = sigmoid(W2 silu(W1 pooled + b1) + b2),
- * x *= gate in place.  x [n,hw,c] bf16, pooled [n,c] fp32, w1 [sq,c], b1 [sq], w2t [sq,c] (= fc2 weight transposed), b2 [c],
- * gate_ws [n,c] fp32 workspace (receives the gate). */
-EWVIT_API int ewvit_se_apply_nhwc_bf16(void *x, const float *pooled, const float *w1, const float *b1, const float *w2t,
-                                       const float *b2, int n, int hw, int c, int sq, float *gate_ws, void *stream);
-
-/* Squeeze-excitation gate only: gate[n, c] = sigmoid(W2 silu(W1 pooled[n] + b1) + b2) (same operands as
- * ewvit_se_apply_nhwc_bf16); the scaling itself is then fused into ewvit_conv1x1_gated_nhwc_bf16.
+/* Squeeze-excitation gate (torchvision.ops.SqueezeExcitation with SiLU / Sigmoid; efficientnet_pytorch's _se_reduce / _se_expand):
+ * gate[n, c] = sigmoid(W2 silu(W1 pooled[n] + b1) + b2) with w1 [sq, c], b1 [sq], w2t [sq, c] (= fc2 weight transposed), b2 [c];
+ * the scaling x * gate itself is fused into ewvit_conv1x1_gated_nhwc_bf16.
  * pooled [n, pool_parts, c]: partial means as written by ewvit_dwconv_nhwc_bf16, summed here in index order (pool_parts = 1:
  * plain [n, c] means).  gate_bf16 != 0: the gates are written as bf16 (what the gated conv multiplies fastest), else fp32. */
 EWVIT_API int ewvit_se_gate_fwd(const float *pooled, int pool_parts, const float *w1, const float *b1, const float *w2t, const float *b2,

@@ -220,19 +220,6 @@ def test_depthwise_general(ops, c, k, stride, hw, same_tf):
         _close(gate, gref, tol=1e-3, bf16_out=False)
 
 
-def test_se_apply(ops):
-    n, c, sq, h, w = 4, 960, 40, 14, 14
-    x = seeded_randn((n, c, h, w), 14).bfloat16()
-    w1, b1 = seeded_randn((sq, c), 15) * c ** -0.5, seeded_randn((sq,), 16)
-    w2, b2 = seeded_randn((c, sq), 17) * sq ** -0.5, seeded_randn((c,), 18)
-    pooled = x.float().mean(dim=(2, 3))
-    gate = torch.sigmoid(F.silu(pooled @ w1.t() + b1) @ w2.t() + b2)
-    ref = x.float() * gate.view(n, c, 1, 1)
-    xd = _nhwc(x).cuda()
-    ops.se_apply(xd, pooled.cuda(), w1.cuda(), b1.cuda(), w2.t().contiguous().cuda(), b2.cuda())
-    _close(xd.permute(0, 3, 1, 2), ref, tol=1e-3)
-
-
 @pytest.mark.parametrize("c,cout,hw,res", [(960, 160, (14, 14), True), (1536, 256, (7, 7), True), (256, 128, (14, 14), False),
                                            (768, 160, (14, 14), False)])
 def test_gated_project_conv(ops, c, cout, hw, res):
