@@ -60,7 +60,7 @@ struct Cfg {
     // 300-900 cycles per tile for the group two tiles back; four stages absorb that latency
     static constexpr int kAccStages = kEpi == EPI_CONV ? 4 : 2;
     static constexpr int kStagingBytes = kEpiWarps * kStgBytes * kStgBufs;
-    static constexpr int kOperandBytes = (kWideEpi ? 160 : kBuilder ? 192 : kEpi == EPI_CONV ? 184 : 200) * 1024;  // operand stages (+ halo buffers)
+    static constexpr int kOperandBytes = (kWideEpi ? 160 : kBuilder ? 192 : kEpi == EPI_CONV ? 192 : 200) * 1024;  // operand stages (+ halo buffers)
     static constexpr int kGateOff = kOperandBytes + kStagingBytes;       // builder kernels: staged SE gates
     static constexpr int kPayloadBytes = kGateOff + (kBuilder ? kGateBytes : 0);  // barriers live right behind
     static constexpr int kSmemBytes = kPayloadBytes + 1024 /*align slack*/ + 512 /*barriers*/;

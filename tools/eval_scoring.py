@@ -53,7 +53,8 @@ def main():
         return model(x, BATCH_SIZE, "dynamic")["logits"]
 
     with torch.no_grad():
-        score(make_videos([lo])[:, :64])                     # warm-up (kernel attributes, workspaces)
+        ids0 = list(range(lo, min(lo + PER_CALL, hi)))
+        score(make_videos(ids0))                             # warm-up at the full call shape (kernel attributes, 512-frame workspaces)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
