@@ -60,10 +60,12 @@ struct Cfg {
     // 300-900 cycles per tile for the group two tiles back; four stages absorb that latency
     static constexpr int kAccStages = kEpi == EPI_CONV ? 4 : 2;
     static constexpr int kStagingBytes = kEpiWarps * kStgBytes * kStgBufs;
-    static constexpr int kOperandBytes = (kWideEpi ? 160 : kBuilder ? 192 : kEpi == EPI_CONV ? 192 : 200) * 1024;  // operand stages (+ halo buffers)
+    static constexpr int kOperandBytes = (kWideEpi ? 160 : kBuilder ? 192 : kEpi == EPI_CONV ? 184 : 200) * 1024;  // operand stages (+ halo buffers)
     static constexpr int kGateOff = kOperandBytes + kStagingBytes;       // builder kernels: staged SE gates
     static constexpr int kPayloadBytes = kGateOff + (kBuilder ? kGateBytes : 0);  // barriers live right behind
     static constexpr int kSmemBytes = kPayloadBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+    // 227 KB opt-in limit covers dynamic + static shared memory (s_scale/s_shift for kBN = 256: 4 KB, + the builder tables)
+    static_assert(kSmemBytes + 4096 + 512 <= 227 * 1024, "operand region too large: cudaFuncSetAttribute would fail");
 };
 
 enum { A_FLAT = 0, A_TILE4D = 1, A_IM2COL = 2, A_SCALED = 3 };
