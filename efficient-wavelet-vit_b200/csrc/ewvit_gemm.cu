@@ -45,7 +45,7 @@ constexpr int kGateChunks = kGateBytes / 16 / (32 * kBuilderWarps);   // 16-byte
 // scheduler), and twice the warps hide twice the latency.  Only the backbone's plain 1x1 convs (EPI_BB without
 // builders: K <= 256) do this: their operand ring can be shallow, which pays for the second set of staging buffers.
 // Builder kernels keep two groups (register file); the long-K MWT convs and the linears keep the deep ring.
-template <int kEpi, bool kBuilder>
+template <int kEpi, bool kBuilder, int kBN = 128>
 struct Cfg {
     static constexpr bool kWideEpi = kEpi == EPI_BB && !kBuilder;
     static constexpr int kEpiWarps = kWideEpi ? 16 : 8;
@@ -191,15 +191,15 @@ __device__ __forceinline__ bool decode_tile(const GemmParams &p, int w, int &m_t
 // reads 4 KB of A and 2 KB of B from its shared memory instead of 4 + 4, and the ring slot shrinks from 65 KB to 41 KB
 // (multiscale conv: 3 -> 4 stages; fusion conv with resident weights: 72 KB instead of 144 KB resident, 3 -> 7 windows in flight).
 template <int kEpi, bool kBuilder, int kBN, int kFast = 0, bool kPair = false>
-__global__ void __launch_bounds__(Cfg<kEpi, kBuilder>::kThreads, 1)
+__global__ void __launch_bounds__(Cfg<kEpi, kBuilder, kBN>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    constexpr int kEpiWarps = Cfg<kEpi, kBuilder>::kEpiWarps, kHalves = Cfg<kEpi, kBuilder>::kHalves;
-    constexpr int kOperandBytes = Cfg<kEpi, kBuilder>::kOperandBytes;
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + Cfg<kEpi, kBuilder>::kPayloadBytes);
-    constexpr int kAccStages = Cfg<kEpi, kBuilder>::kAccStages;
+    constexpr int kEpiWarps = Cfg<kEpi, kBuilder, kBN>::kEpiWarps, kHalves = Cfg<kEpi, kBuilder, kBN>::kHalves;
+    constexpr int kOperandBytes = Cfg<kEpi, kBuilder, kBN>::kOperandBytes;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + Cfg<kEpi, kBuilder, kBN>::kPayloadBytes);
+    constexpr int kAccStages = Cfg<kEpi, kBuilder, kBN>::kAccStages;
     unsigned long long *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages,
                        *tempty = bars + 2 * kStages + kMaxAccStages;
     unsigned long long *hfull = bars + 2 * kStages + 2 * kMaxAccStages, *hempty = hfull + kMaxHalo;
@@ -520,7 +520,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // the [frames of the tile][K] gate block is staged once per tile -- its 16-byte chunks are requested one tile
             // AHEAD into registers, so the copy costs two named barriers and no exposed latency.
             const bool gsm = p.a_gate_smem != 0;
-            const uint32_t gate_sm = smem_base + (uint32_t)Cfg<kEpi, kBuilder>::kGateOff;
+            const uint32_t gate_sm = smem_base + (uint32_t)Cfg<kEpi, kBuilder, kBN>::kGateOff;
             const int kchunks = p.a_k >> 3;                       // 16-byte chunks per gate row
             uint4 gpre[kGateChunks];
             auto gate_prefetch = [&](int w2) {
@@ -796,7 +796,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int grp2 = grp & 1;               // which of every two consecutive tiles this group drains
         float *g_scale = s_scale + grp2 * kBN, *g_shift = s_shift + grp2 * kBN;
         constexpr int kColsPerGroup = kBN / kHalves;
-        const uint32_t stg = smem_base + kOperandBytes + (uint32_t)(warp - 2) * kStgBytes * Cfg<kEpi, kBuilder>::kStgBufs;
+        const uint32_t stg = smem_base + kOperandBytes + (uint32_t)(warp - 2) * kStgBytes * Cfg<kEpi, kBuilder, kBN>::kStgBufs;
         int cur_nt = -1;
         int it = 0;
         for (int w = w_first; w < w_total; w += w_step, ++it) {
@@ -1150,13 +1150,13 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
     int dev = 0;
     EWVIT_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        EWVIT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kBuilder, kBN, kFast, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kEpi, kBuilder>::kSmemBytes));
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kBuilder, kBN, kFast, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kEpi, kBuilder, kBN>::kSmemBytes));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     if (p.b_tile_bytes <= 0) p.b_tile_bytes = kBN * BK * 2;
     if (p.stage_bytes <= 0) p.stage_bytes = kTileBytes + p.b_tile_bytes;
     if (p.stages <= 0) {
-        p.stages = Cfg<kEpi, kBuilder>::kOperandBytes / p.stage_bytes;
+        p.stages = Cfg<kEpi, kBuilder, kBN>::kOperandBytes / p.stage_bytes;
         if (p.stages > 6) p.stages = 6;
     }
     // plain (one-tap-per-slot) paths with a single column tile and a small weight matrix: keep all of B resident and let
@@ -1166,7 +1166,7 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
         p.num_kb * p.b_tile_bytes <= 96 * 1024 && p.stage_bytes == kTileBytes + p.b_tile_bytes) {
         p.b_res = 1;
         p.stage_bytes = kTileBytes;
-        p.stages = (Cfg<kEpi, kBuilder>::kOperandBytes - p.num_kb * p.b_tile_bytes) / kTileBytes;
+        p.stages = (Cfg<kEpi, kBuilder, kBN>::kOperandBytes - p.num_kb * p.b_tile_bytes) / kTileBytes;
         if (p.stages > kStages) p.stages = kStages;
         p.bres_off = p.stages * kTileBytes;
     }
@@ -1182,8 +1182,8 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
         if (clusters <= 0) return EWVIT_OK;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(2 * clusters));
-        cfg.blockDim = dim3(Cfg<kEpi, kBuilder>::kThreads);
-        cfg.dynamicSmemBytes = Cfg<kEpi, kBuilder>::kSmemBytes;
+        cfg.blockDim = dim3(Cfg<kEpi, kBuilder, kBN>::kThreads);
+        cfg.dynamicSmemBytes = Cfg<kEpi, kBuilder, kBN>::kSmemBytes;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1198,7 +1198,7 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
     }
     if (grid > work) grid = work;
     if (grid <= 0) return EWVIT_OK;
-    gemm_tc_kernel<kEpi, kBuilder, kBN, kFast><<<(unsigned)grid, Cfg<kEpi, kBuilder>::kThreads, Cfg<kEpi, kBuilder>::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+    gemm_tc_kernel<kEpi, kBuilder, kBN, kFast><<<(unsigned)grid, Cfg<kEpi, kBuilder, kBN>::kThreads, Cfg<kEpi, kBuilder, kBN>::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }
@@ -1663,6 +1663,9 @@ extern "C" int ewvit_conv_nhwc_bf16_ex(const void *x, const void *w, int n, int 
 // overlapping 64-wide windows.  Measured: the kernel time did NOT change (0.19 ms per 256 frames either way) -- a tiled TMA load
 // costs ~3 cycles per box ROW whatever the row length (408 rows per tile in both layouts), and with the loads replaced by
 // cp.async copies (tried, dropped) the per-tile cost of the epilogue (~2400 cycles per 128 x 64 tile and group) is next in line.
+// Round 2: with the epilogue switched off the kernel still needs 322 of its 372 us per 512 frames (tools/trace_head.py), and a
+// variant with four epilogue groups (64-column tiles, 16 epilogue warps) measured no faster: the producer's ~1700 cycles per tile
+// (three 136-row boxes of 32-byte rows) are the bound.
 //   w [64, 144] bf16: w[g*18+oc][(dy*3 + dx)*16 + g*3+ic] = seperate[g].weight[oc][ic][dy][dx], zero elsewhere
 //   scale/shift [64] fp32 (folded BN, zeros past 54);  y [n, h+2, wd+2, 64] bf16 padded-flat (border written as zeros)
 extern "C" int ewvit_mwt_head_conv_fwd(const void *up, const void *w, int n, int h, int wd, const float *scale, const float *shift,
