@@ -25,47 +25,68 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// y[f][j] = sum_k Wt[k*ldw + j] * x[f][k]   for the kFpc frames of the CTA (x in shared memory), k ascending, one fmaf per term.
-// The weight column is requested 64 rows at a time (64 independent, coalesced L2 loads in flight per thread).  The first
-// version asked for 16 at a time from a 128-thread CTA that ran its 28 projections one after the other: ~230 dependent L2
+// y[f][j] = sum_k Wt[k*ldw + j] * x[k][f]   for the kFpc frames of the CTA, k ascending, one fmaf per term.
+// Activations live in shared memory CHANNEL-major, x[k][kFpc]: one 16-byte broadcast read brings the four frames' values of
+// channel k (frame-major rows cost four 4-byte reads per weight and the shared-memory pipe bounded the kernel).
+// The first version asked for 16 weight rows at a time from a 128-thread CTA that ran its 28 projections one after the other: ~230 dependent L2
 // round trips per CTA with four warps per SM to hide them -- 0.34 ms per 512 frames for 0.17 GFMA.
-__device__ __forceinline__ void matvec_t(const float *__restrict__ wt, int ldw, int in_dim, const float *x, int ldx, int j,
-                                         float (&acc)[kFpc]) {
+static_assert(kFpc == 4, "activations are read as float4 = the four frames of a channel");
+__device__ __forceinline__ float ldg_nc(const float *ptr) {       // volatile: keeps the batch of loads where it is written
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(ptr));
+    return v;
+}
+// in_dim % 32 == 0 (the launcher requires d % 32 == 0).  Chunks of 32 weight rows, the NEXT chunk requested before the FMAs
+// of the current one: 32..64 independent, coalesced L2 loads in flight per thread.
+__device__ __forceinline__ void matvec_t(const float *__restrict__ wt, int ldw, int in_dim, const float *x, int j, float (&acc)[kFpc]) {
 #pragma unroll
     for (int f = 0; f < kFpc; ++f) acc[f] = 0.f;
-    for (int k0 = 0; k0 < in_dim; k0 += 64) {
-        float w[64];
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    const float *wp = wt + j;
+    float wc[32], wn[32];
 #pragma unroll
-        for (int u = 0; u < 64; ++u) w[u] = k0 + u < in_dim ? __ldg(wt + (long long)(k0 + u) * ldw + j) : 0.f;
+    for (int u = 0; u < 32; ++u) wc[u] = ldg_nc(wp + (long long)u * ldw);
+    for (int k0 = 0; k0 < in_dim; k0 += 32) {
+        if (k0 + 32 < in_dim) {
 #pragma unroll
-        for (int u = 0; u < 64; ++u) {
-            if (k0 + u < in_dim) {
-#pragma unroll
-                for (int f = 0; f < kFpc; ++f) acc[f] = fmaf(w[u], x[f * ldx + k0 + u], acc[f]);
-            }
+            for (int u = 0; u < 32; ++u) wn[u] = ldg_nc(wp + (long long)(k0 + 32 + u) * ldw);
         }
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+            const float4 xv = x4[k0 + u];
+            acc[0] = fmaf(wc[u], xv.x, acc[0]);
+            acc[1] = fmaf(wc[u], xv.y, acc[1]);
+            acc[2] = fmaf(wc[u], xv.z, acc[2]);
+            acc[3] = fmaf(wc[u], xv.w, acc[3]);
+        }
+#pragma unroll
+        for (int u = 0; u < 32; ++u) wc[u] = wn[u];
     }
 }
 
 // blockDim.x = G * D: thread (g, j) = group g, output column j.  Independent projections are dealt to the groups round-robin
 // (q | k,v of the query tokens | k,v of the context: five per cross-attention; fusion conv | gate MLP at the end), so the
-// dependent chain of a CTA is 2 projections per cross-attention instead of 7.  Every output is still ONE thread's fmaf chain
+// dependent chain of a CTA is 3 projections per cross-attention instead of 7.  Every output is still ONE thread's fmaf chain
 // over k ascending: results are bit-identical to the single-group version whatever G is.
+#define AT(c, f) ((c) * kFpc + (f))      // channel-major activations
+// kD = 128 (the shipped dama_dim): row pitches of the weight matrices are compile-time constants, so the 64 weight addresses of a
+// thread are immediates off one base register; kD = 0: any d % 32 == 0.
+template <int kD>
 __global__ void __launch_bounds__(kMaxGroups * 128) dama_tail_kernel(const DamaParams p) {
-    extern __shared__ float sm[];
-    const int D = p.d, G = blockDim.x / D;
+    extern __shared__ __align__(16) float sm[];
+    const int D = kD ? kD : p.d, G = blockDim.x / D;
     const int g = threadIdx.x / D, j = threadIdx.x - g * D;
-    float *s_s = sm;                 // [kFpc][D] spatial tokens
+    float *s_s = sm;                 // [D][kFpc] spatial tokens
     float *s_f = s_s + kFpc * D;     // frequency tokens
     float *s_xn = s_f + kFpc * D;    // normalised query tokens
     float *s_q = s_xn + kFpc * D;
     float *s_k0 = s_q + kFpc * D, *s_k1 = s_k0 + kFpc * D, *s_v0 = s_k1 + kFpc * D, *s_v1 = s_v0 + kFpc * D;
     float *s_p0 = s_v1 + kFpc * D, *s_p1 = s_p0 + kFpc * D;   // per-channel q*k products
     float *s_att = s_p1 + kFpc * D;
-    float *s_cat = s_att + kFpc * D;   // [kFpc][2D]
+    float *s_cat = s_att + kFpc * D;   // [2D][kFpc]
     float *s_hid = s_cat + kFpc * 2 * D;   // [kFpc][D/2]
     float *s_gate = s_hid + kFpc * (D / 2);   // [kFpc][4]
-    float *s_fus = s_gate + kFpc * 4;          // [kFpc][D] fusion-gate features
+    float *s_fus = s_gate + kFpc * 4;          // [D][kFpc] fusion-gate features
 
     const long long f0 = (long long)blockIdx.x * kFpc;
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -73,9 +94,10 @@ __global__ void __launch_bounds__(kMaxGroups * 128) dama_tail_kernel(const DamaP
     const float scale = rsqrtf((float)dh);
 
     for (int i = threadIdx.x; i < kFpc * D; i += blockDim.x) {
-        const long long fr = f0 + i / D;
-        s_s[i] = fr < p.n ? p.space_in[fr * D + (i % D)] : 0.f;
-        s_f[i] = fr < p.n ? p.freq_in[fr * D + (i % D)] : 0.f;
+        const int f = i / D, c = i - f * D;
+        const long long fr = f0 + f;
+        s_s[AT(c, f)] = fr < p.n ? p.space_in[fr * D + c] : 0.f;
+        s_f[AT(c, f)] = fr < p.n ? p.freq_in[fr * D + c] : 0.f;
     }
     __syncthreads();
 
@@ -91,15 +113,15 @@ __global__ void __launch_bounds__(kMaxGroups * 128) dama_tail_kernel(const DamaP
             // LayerNorm of the query tokens (dama.py:71,75), one warp per frame
             for (int f = warp; f < kFpc; f += nwarps) {
                 float s = 0.f;
-                for (int c = lane; c < D; c += 32) s += xq[f * D + c];
+                for (int c = lane; c < D; c += 32) s += xq[AT(c, f)];
                 const float mean = warp_sum(s) / (float)D;
                 float v = 0.f;
                 for (int c = lane; c < D; c += 32) {
-                    const float t = xq[f * D + c] - mean;
+                    const float t = xq[AT(c, f)] - mean;
                     v += t * t;
                 }
                 const float rstd = rsqrtf(warp_sum(v) / (float)D + p.ln_eps);
-                for (int c = lane; c < D; c += 32) s_xn[f * D + c] = (xq[f * D + c] - mean) * rstd * ln_w[c] + ln_b[c];
+                for (int c = lane; c < D; c += 32) s_xn[AT(c, f)] = (xq[AT(c, f)] - mean) * rstd * ln_w[c] + ln_b[c];
             }
             __syncthreads();
 
@@ -109,9 +131,8 @@ __global__ void __launch_bounds__(kMaxGroups * 128) dama_tail_kernel(const DamaP
                 const float *w = t == 0 ? wq_t : (t <= 2 ? wkv_t : wkv_t + D);
                 const float *x = (t == 0 || t == 1 || t == 3) ? s_xn : ctx;
                 float *dst = t == 0 ? s_q : t == 1 ? s_k0 : t == 2 ? s_k1 : t == 3 ? s_v0 : s_v1;
-                matvec_t(w, t == 0 ? D : 2 * D, D, x, D, j, acc);
-#pragma unroll
-                for (int f = 0; f < kFpc; ++f) dst[f * D + j] = acc[f];
+                matvec_t(w, t == 0 ? D : 2 * D, D, x, j, acc);
+                *reinterpret_cast<float4 *>(dst + AT(j, 0)) = make_float4(acc[0], acc[1], acc[2], acc[3]);
             }
             __syncthreads();
             for (int i = threadIdx.x; i < kFpc * D; i += blockDim.x) {
@@ -122,12 +143,12 @@ __global__ void __launch_bounds__(kMaxGroups * 128) dama_tail_kernel(const DamaP
 
             // 1 query x 2 keys per head: softmax over the two dots (dama.py:44-48)
             for (int i = threadIdx.x; i < kFpc * D; i += blockDim.x) {
-                const int f = i / D, c0 = i - f * D;
+                const int c0 = i / kFpc, f = i - c0 * kFpc;
                 const int h0 = (c0 / dh) * dh;
                 float d0 = 0.f, d1 = 0.f;
                 for (int c = 0; c < dh; ++c) {
-                    d0 += s_p0[f * D + h0 + c];
-                    d1 += s_p1[f * D + h0 + c];
+                    d0 += s_p0[AT(h0 + c, f)];
+                    d1 += s_p1[AT(h0 + c, f)];
                 }
                 d0 *= scale;
                 d1 *= scale;
@@ -140,10 +161,10 @@ __global__ void __launch_bounds__(kMaxGroups * 128) dama_tail_kernel(const DamaP
 
             if (g == 0) {
                 float acc[kFpc];
-                matvec_t(wo_t, D, D, s_att, D, j, acc);
+                matvec_t(wo_t, D, D, s_att, j, acc);
                 const float b = bo[j];
 #pragma unroll
-                for (int f = 0; f < kFpc; ++f) xq[f * D + j] += acc[f] + b;   // residual (dama.py:72,76)
+                for (int f = 0; f < kFpc; ++f) xq[AT(j, f)] += acc[f] + b;   // residual (dama.py:72,76)
             }
             __syncthreads();
         }
@@ -154,21 +175,20 @@ __global__ void __launch_bounds__(kMaxGroups * 128) dama_tail_kernel(const DamaP
     const float *f_scale = wf_t + 2LL * D * D, *f_shift = f_scale + D;
     const float *g1_t = f_shift + D, *g1_b = g1_t + 2LL * D * (D / 2);
     const float *g2 = g1_b + D / 2, *g2_b = g2 + 3 * (D / 2);
-    for (int i = threadIdx.x; i < kFpc * D; i += blockDim.x) {
-        const int f = i / D, c = i - f * D;
-        s_cat[f * 2 * D + c] = s_s[i];
-        s_cat[f * 2 * D + D + c] = s_f[i];
+    for (int i = threadIdx.x; i < kFpc * D; i += blockDim.x) {      // cat(space, freq) along the channel axis
+        s_cat[i] = s_s[i];
+        s_cat[kFpc * D + i] = s_f[i];
     }
     __syncthreads();
     // two independent tasks: the fusion conv (D outputs) and the first gate_net layer (D/2 outputs; dama.py:105-113,156-157)
     for (int t = g; t < 2; t += G) {
         float acc[kFpc];
         if (t == 0) {
-            matvec_t(wf_t, D, 2 * D, s_cat, 2 * D, j, acc);
+            matvec_t(wf_t, D, 2 * D, s_cat, j, acc);
 #pragma unroll
-            for (int f = 0; f < kFpc; ++f) s_fus[f * D + j] = fmaxf(fmaf(acc[f], f_scale[j], f_shift[j]), 0.f);
+            for (int f = 0; f < kFpc; ++f) s_fus[AT(j, f)] = fmaxf(fmaf(acc[f], f_scale[j], f_shift[j]), 0.f);
         } else if (j < D / 2) {
-            matvec_t(g1_t, D / 2, 2 * D, s_cat, 2 * D, j, acc);
+            matvec_t(g1_t, D / 2, 2 * D, s_cat, j, acc);
 #pragma unroll
             for (int f = 0; f < kFpc; ++f) s_hid[f * (D / 2) + j] = fmaxf(acc[f] + g1_b[j], 0.f);
         }
@@ -196,13 +216,14 @@ __global__ void __launch_bounds__(kMaxGroups * 128) dama_tail_kernel(const DamaP
         const int f = i / D, c = i - f * D;
         const long long fr = f0 + f;
         if (fr < p.n) {
-            const float sv = s_s[i], fv = s_f[i];
-            p.fused[fr * D + c] = s_gate[f * 4] * sv + s_gate[f * 4 + 1] * fv + s_gate[f * 4 + 2] * s_fus[i];   // dama.py:159-163
+            const float sv = s_s[AT(c, f)], fv = s_f[AT(c, f)];
+            p.fused[fr * D + c] = s_gate[f * 4] * sv + s_gate[f * 4 + 1] * fv + s_gate[f * 4 + 2] * s_fus[AT(c, f)];   // dama.py:159-163
             p.space[fr * D + c] = sv;
             p.freq[fr * D + c] = fv;
         }
     }
 }
+#undef AT
 
 // Per-video mean over K consecutive frames (dama.py:188-199) and, when cw1 != nullptr, the classifier
 // Linear(D->Hc)+ReLU+Linear(Hc->1) on the first feature set (model.py:62-68,92).  One CTA per video.
@@ -270,10 +291,12 @@ extern "C" int ewvit_dama_tail_fwd(const float *space_in, const float *freq_in, 
     int dev = 0;
     EWVIT_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        EWVIT_CUDA_OK(cudaFuncSetAttribute(dama_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(dama_tail_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(dama_tail_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    dama_tail_kernel<<<(unsigned)((n + kFpc - 1) / kFpc), groups * d, smem, (cudaStream_t)stream>>>(p);
+    if (d == 128) dama_tail_kernel<128><<<(unsigned)((n + kFpc - 1) / kFpc), groups * d, smem, (cudaStream_t)stream>>>(p);
+    else dama_tail_kernel<0><<<(unsigned)((n + kFpc - 1) / kFpc), groups * d, smem, (cudaStream_t)stream>>>(p);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }
