@@ -215,14 +215,15 @@ def load_peaks():
 
 def load_ncu_traffic(key, frames):
     """dram__bytes_read.sum + dram__bytes_write.sum of the named kernel from the latest committed `ncu --set full` capture
-    (profiles/<tag>_traffic.json, written by tools/make_profile_md.py), scaled to this run's frames per launch; None if
+    (profiles/<tag>_traffic.json, written by tools/make_profile_md.py), scaled linearly to this run's frames per launch (the capture may hold fewer frames: ncu replays are expensive); None if
     there is no capture."""
     import glob
     files = sorted(glob.glob(os.path.join(REPO, "profiles", "*_traffic.json")))
     if not files:
         return None
     try:
-        rec = json.load(open(files[-1])).get(key)
+        recs = json.load(open(files[-1]))
+        rec = recs.get(key) or next((v for k, v in sorted(recs.items()) if k.startswith(key.split("_")[0] + "_")), None)   # any frame count
         return None if rec is None else rec["dram_bytes"] * frames / rec["frames"]
     except (OSError, ValueError, KeyError):
         return None

@@ -64,11 +64,13 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const TIn *__restrict__ 
         // pad = 1: padded-flat output [n, ho+2, wo+2, cout] (interior written, the zero border belongs to the caller)
         __nv_bfloat16 *py = y + ((img * (ho + 2 * pad) + oy + pad) * (wo + 2 * pad) + ox0 + pad) * cout;
         for (int c0 = 0; c0 < cout; c0 += 8) {
-            float acc[kStemPx][8];
+            // packed fp32x2 FMAs (FFMA2: each half rounds exactly like fmaf): a three-register FFMA issues every other cycle on
+            // sm_100, so the 648 FMAs per output pixel bound this kernel at half the fp32 rate
+            float2 acc[kStemPx][4];
 #pragma unroll
             for (int p4 = 0; p4 < kStemPx; ++p4)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[p4][j] = s_b[c0 + j];
+                for (int j = 0; j < 4; ++j) acc[p4][j] = make_float2(s_b[c0 + 2 * j], s_b[c0 + 2 * j + 1]);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -78,13 +80,16 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const TIn *__restrict__ 
                         const int k = c * 9 + dy * 3 + dx;
                         const float4 w0 = *reinterpret_cast<const float4 *>(&s_w[k * kStemMaxC + c0]);
                         const float4 w1 = *reinterpret_cast<const float4 *>(&s_w[k * kStemMaxC + c0 + 4]);
+                        const float2 wa = make_float2(w0.x, w0.y), wb = make_float2(w0.z, w0.w);
+                        const float2 wc = make_float2(w1.x, w1.y), wd2 = make_float2(w1.z, w1.w);
 #pragma unroll
                         for (int p4 = 0; p4 < kStemPx; ++p4) {
                             const float v = in[c][dy][2 * p4 + dx];
-                            acc[p4][0] = fmaf(w0.x, v, acc[p4][0]); acc[p4][1] = fmaf(w0.y, v, acc[p4][1]);
-                            acc[p4][2] = fmaf(w0.z, v, acc[p4][2]); acc[p4][3] = fmaf(w0.w, v, acc[p4][3]);
-                            acc[p4][4] = fmaf(w1.x, v, acc[p4][4]); acc[p4][5] = fmaf(w1.y, v, acc[p4][5]);
-                            acc[p4][6] = fmaf(w1.z, v, acc[p4][6]); acc[p4][7] = fmaf(w1.w, v, acc[p4][7]);
+                            const float2 vv = make_float2(v, v);
+                            acc[p4][0] = __ffma2_rn(wa, vv, acc[p4][0]);
+                            acc[p4][1] = __ffma2_rn(wb, vv, acc[p4][1]);
+                            acc[p4][2] = __ffma2_rn(wc, vv, acc[p4][2]);
+                            acc[p4][3] = __ffma2_rn(wd2, vv, acc[p4][3]);
                         }
                     }
 #pragma unroll
@@ -92,10 +97,13 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const TIn *__restrict__ 
                 if (ox0 + p4 >= wo) break;
                 float o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float th;
-                    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(acc[p4][j]));
-                    o[j] = fmaf(acc[p4][j], th, acc[p4][j]);
+                for (int j = 0; j < 4; ++j) {
+                    float2 th;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(acc[p4][j].x));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(acc[p4][j].y));
+                    const float2 r = __ffma2_rn(acc[p4][j], th, acc[p4][j]);
+                    o[2 * j] = r.x;
+                    o[2 * j + 1] = r.y;
                 }
                 uint4 pk;
                 __nv_bfloat162 b0 = __floats2bfloat162_rn(o[0], o[1]), b1 = __floats2bfloat162_rn(o[2], o[3]);
@@ -194,51 +202,51 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __grid_constant
             const int g = item % G;
             const int t = item / G;
             const int ox = t % wo, fl = t / wo;
-            float wr[9][4], br[4], sum[4];
+            // channel pairs as float2: packed fp32x2 FMAs (FFMA2, each half rounds exactly like fmaf) -- a three-register FFMA issues
+            // every other cycle on sm_100, and 36 of them per 4-channel output made the FMA pipe a co-limiter of this kernel
+            float2 wr[9][2], br[2], sum[2];
             const uint32_t wbase = ewvit::smem_u32(s_w) + g * 16;
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
                 const float4 v = lds128f(wbase + k * SC * 4);
-                wr[k][0] = v.x; wr[k][1] = v.y; wr[k][2] = v.z; wr[k][3] = v.w;
+                wr[k][0] = make_float2(v.x, v.y); wr[k][1] = make_float2(v.z, v.w);
             }
             {
                 const float4 v = lds128f(wbase + 9 * SC * 4);
-                br[0] = v.x; br[1] = v.y; br[2] = v.z; br[3] = v.w;
+                br[0] = make_float2(v.x, v.y); br[1] = make_float2(v.z, v.w);
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sum[j] = 0.f;
+            sum[0] = sum[1] = make_float2(0.f, 0.f);
             uint32_t rp = sb + (uint32_t)fl * plane_bytes + (uint32_t)(ox * STRIDE) * (SC * 2) + g * 8;   // padded (row 0, first tap column)
             const bool live = f + fl < n;
             __nv_bfloat16 *py = y + ((long long)(f + fl) * npix + ox) * c + cs + g * 4;
-            auto load_row = [&](float (&r)[3][4]) {      // the next padded row of this column's three taps
+            auto load_row = [&](float2 (&r)[3][2]) {      // the next padded row of this column's three taps
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
                     const uint2 v = lds64(rp + dx * (SC * 2));
-                    r[dx][0] = __uint_as_float(v.x << 16);
-                    r[dx][1] = __uint_as_float(v.x & 0xffff0000u);
-                    r[dx][2] = __uint_as_float(v.y << 16);
-                    r[dx][3] = __uint_as_float(v.y & 0xffff0000u);
+                    r[dx][0] = make_float2(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u));
+                    r[dx][1] = make_float2(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
                 }
                 rp += row_bytes;
             };
-            auto emit = [&](const float (&r0)[3][4], const float (&r1)[3][4], const float (&r2)[3][4]) {
-                float a[4];
+            auto emit = [&](const float2 (&r0)[3][2], const float2 (&r1)[3][2], const float2 (&r2)[3][2]) {
+                float2 a[2];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float hv = br[j];                   // h = v/2 (weights and bias are pre-halved)
+                for (int j = 0; j < 2; ++j) {
+                    float2 hv = br[j];                  // h = v/2 (weights and bias are pre-halved)
 #pragma unroll
                     for (int dx = 0; dx < 3; ++dx) {
-                        hv = fmaf(wr[dx][j], r0[dx][j], hv);
-                        hv = fmaf(wr[3 + dx][j], r1[dx][j], hv);
-                        hv = fmaf(wr[6 + dx][j], r2[dx][j], hv);
+                        hv = __ffma2_rn(wr[dx][j], r0[dx][j], hv);
+                        hv = __ffma2_rn(wr[3 + dx][j], r1[dx][j], hv);
+                        hv = __ffma2_rn(wr[6 + dx][j], r2[dx][j], hv);
                     }
-                    float th;
-                    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hv));
-                    a[j] = fmaf(hv, th, hv);
-                    sum[j] += a[j];
+                    float2 th;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(hv.x));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(hv.y));
+                    a[j] = __ffma2_rn(hv, th, hv);
+                    sum[j] = __fadd2_rn(sum[j], a[j]);
                 }
                 if (live) {
-                    const __nv_bfloat162 p0 = __floats2bfloat162_rn(a[0], a[1]), p1 = __floats2bfloat162_rn(a[2], a[3]);
+                    const __nv_bfloat162 p0 = __floats2bfloat162_rn(a[0].x, a[0].y), p1 = __floats2bfloat162_rn(a[1].x, a[1].y);
                     uint2 pk;
                     pk.x = *reinterpret_cast<const uint32_t *>(&p0);
                     pk.y = *reinterpret_cast<const uint32_t *>(&p1);
@@ -246,7 +254,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __grid_constant
                 }
                 py += ystep;
             };
-            float ra[3][4], rb[3][4], rc[3][4];
+            float2 ra[3][2], rb[3][2], rc[3][2];
             if (STRIDE == 1) {
                 load_row(ra);
                 load_row(rb);
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __grid_constant
                     if (oy + 1 < ho) { load_row(rb); load_row(ra); emit(rc, rb, ra); }
                 }
             }
-            *reinterpret_cast<float4 *>(ssum + (fl * wo + ox) * SC + g * 4) = make_float4(sum[0], sum[1], sum[2], sum[3]);
+            *reinterpret_cast<float4 *>(ssum + (fl * wo + ox) * SC + g * 4) = make_float4(sum[0].x, sum[0].y, sum[1].x, sum[1].y);
         }
         __syncthreads();    // column sums are complete and everyone is done reading this stage buffer
         if (pooled) {
@@ -442,7 +450,9 @@ __global__ void __launch_bounds__(256, 3) conv3x3_c24_kernel(const __nv_bfloat16
 // ---- squeeze-excitation gate: gate[n, c] = sigmoid(W2 * silu(W1 * pooled[n] + b1) + b2).
 //      One CTA serves kSeF frames, so each weight matrix (up to 0.4 MB at c = 1536) is pulled from L2 once per kSeF
 //      frames; both layers read the weights as float4 with several independent loads in flight per thread (the
-//      first version was a chain of dependent L2 round trips: ~50 us per launch for ~1 MFLOP).
+//      first version was a chain of dependent L2 round trips: ~50 us per launch for ~1 MFLOP).  Round 2 tried eight frames per
+//      CTA (half the L2 traffic: 33 us instead of 21 at c = 1536) and clusters of four CTAs splitting both weight matrices with
+//      the hidden units exchanged through distributed shared memory (25 us): neither the L2 bytes nor the weight reads bound it.
 constexpr int kSeF = 4;
 constexpr int kSeThreads = 512;
 constexpr int kSeMaxC = 12 * 128;          // FC1 keeps one weight row (c / 128 float4 per lane) in registers

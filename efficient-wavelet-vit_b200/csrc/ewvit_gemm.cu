@@ -45,9 +45,12 @@ constexpr int kGateChunks = kGateBytes / 16 / (32 * kBuilderWarps);   // 16-byte
 // scheduler), and twice the warps hide twice the latency.  Only the backbone's plain 1x1 convs (EPI_BB without
 // builders: K <= 256) do this: their operand ring can be shallow, which pays for the second set of staging buffers.
 // Builder kernels keep two groups (register file); the long-K MWT convs and the linears keep the deep ring.
+// The three-level MWT head conv (EPI_CONV with a 192-column tile = 3 levels x 64 channels: 27 K = 16 MMAs per tile) is all epilogue
+// as well -- 128 x 192 outputs per ~900 cycles of MMA -- and gets the four groups, too.
 template <int kEpi, bool kBuilder, int kBN = 128>
 struct Cfg {
-    static constexpr bool kWideEpi = kEpi == EPI_BB && !kBuilder;
+    static constexpr bool kHead3 = kEpi == EPI_CONV && kBN == 192;
+    static constexpr bool kWideEpi = (kEpi == EPI_BB && !kBuilder) || kHead3;
     static constexpr int kEpiWarps = kWideEpi ? 16 : 8;
     static constexpr int kEpiGroups = kEpiWarps / 4;
     static constexpr int kHalves = kEpiGroups / 2;                       // column halves per accumulator stage
@@ -58,9 +61,9 @@ struct Cfg {
     // TMEM accumulator stages.  The MWT convs (128 columns per tile) use all 512 columns = 4 stages: the two epilogue groups have the
     // throughput (one tile per ~2500 cycles each against one per ~2200 of the issuer) but with two stages the issuer still waited
     // 300-900 cycles per tile for the group two tiles back; four stages absorb that latency
-    static constexpr int kAccStages = kEpi == EPI_CONV ? 4 : 2;
+    static constexpr int kAccStages = (kEpi == EPI_CONV && !kHead3) ? 4 : 2;
     static constexpr int kStagingBytes = kEpiWarps * kStgBytes * kStgBufs;
-    static constexpr int kOperandBytes = (kWideEpi ? 160 : kBuilder ? 192 : kEpi == EPI_CONV ? 184 : 200) * 1024;  // operand stages (+ halo buffers)
+    static constexpr int kOperandBytes = (kHead3 ? 144 : kWideEpi ? 160 : kBuilder ? 192 : kEpi == EPI_CONV ? 184 : 200) * 1024;  // operand stages (+ halo buffers)
     static constexpr int kGateOff = kOperandBytes + kStagingBytes;       // builder kernels: staged SE gates
     static constexpr int kPayloadBytes = kGateOff + (kBuilder ? kGateBytes : 0);  // barriers live right behind
     static constexpr int kSmemBytes = kPayloadBytes + 1024 /*align slack*/ + 512 /*barriers*/;
@@ -111,8 +114,8 @@ struct GemmParams {
     int a_gate_bf16;
     int a_hw;              // rows (pixels) per frame
     int a_k;               // K = row pitch of A and of the gate
-    int k16;               // flat3 with 16 channels per pixel (MWT head conv): a pixel is ONE 32-byte row = one MMA K step; the window
-                           // of a vertical tap is 136 rows x 32 bytes (32B swizzle) and every (dy, dx) tap is a single MMA on it
+    int k16;               // 2 = the three-level MWT head conv: flat3 with 32 channels per pixel, a pixel is ONE 64-byte row = two MMA K steps;
+                           // the window of a vertical tap is 136 rows x 64 bytes (64B swizzle), the weight tiles are [128, 16] (32B swizzle)
     int pair;              // CTA pairs on cta_group::2 (MWT flat3 convs, backbone 1x1 convs): every CTA stores b_half filter rows per B tile
     int b_half;            // pair mode: rows of a B tile held by each CTA = half of the MMA's N
     int a_gate_smem;       // the gates of a tile's frames are staged in shared memory once per tile (bf16 gates, <= kGateFrames frames per tile)
@@ -206,7 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     unsigned long long *bres_bar = hempty + kMaxHalo;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bres_bar + 1);
     const uint32_t kBTileB = (uint32_t)p.b_tile_bytes;    // B tile: b_rows x 64 bf16 (b_rows = kBN, or the 16-aligned N of a single column tile)
-    constexpr uint32_t kTmemColsT = kAccStages * kBN;
+    constexpr uint32_t kTmemColsT = kAccStages * kBN <= 256 ? 256 : 512;      // allocations are powers of two (2 x 192 -> 512)
     __shared__ __align__(16) float s_scale[2 * kBN], s_shift[2 * kBN];
     __shared__ int s_koff[kBuilder ? 9 * 8 : 1];
     __shared__ __align__(16) uint32_t s_zero[4];
@@ -279,7 +282,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t phase = 0, hphase = 0;
         int tt = 0;
         if (p.b_res) {     // weights are small and identical for every tile: fetch all k-blocks once
-            const int nb = p.flat3 ? 3 * p.num_kb : p.num_kb;    // flat3: num_kb counts (dy, chunk) slots of three taps each
+            // flat3: num_kb counts (dy, chunk) slots of three taps each; the three-level head conv keeps two K = 16 tiles per tap
+            const int nb = p.k16 == 2 ? 6 * p.num_kb : p.flat3 ? 3 * p.num_kb : p.num_kb;
             const int kstep = p.k16 ? 16 : BK;
             if (ewvit::elect_one()) {
                 const uint32_t bb = ewvit::smem_u32(bres_bar);
@@ -379,7 +383,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // plain 1x1 conv on a CTA pair: both CTAs' tiles of this slot complete on the LEADER's full barrier
                     if (ewvit::elect_one()) {
                         if (cta_rank == 0) ewvit::mbar_expect_tx(bar, 2 * kStageB);
-                        ewvit::tma_load_2d_pair(a_dst, &tmA, chunk * BK, m_t * BM + p.tap_a0[tap], bar);
+                        if (p.a_mode == A_TILE4D)      // stride-1|2 box path on a pair: each CTA fetches the pixel box of ITS tile
+                            ewvit::tma_load_4d_pair(a_dst, &tmA, chunk * BK, ax0 + p.tap_a0[tap], ay0 + p.tap_a1[tap], img, bar);
+                        else
+                            ewvit::tma_load_2d_pair(a_dst, &tmA, chunk * BK, m_t * BM + p.tap_a0[tap], bar);
                         if (!p.b_res) ewvit::tma_load_2d_pair(a_dst + kTileBytes, &tmB, kb * BK, n_t * kBN + (int)cta_rank * p.b_half, bar);
                     }
                 } else if (ewvit::elect_one()) {
@@ -417,7 +424,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int n_valid = min(kBN, p.N - n_t * kBN);
             // pair mode splits B by HALF OF THE MMA's N: with several column tiles every CTA holds kBN / 2 rows, so N stays kBN
             // (rows past the tensor are zero-filled)
-            const uint32_t idesc = ewvit::umma_idesc_bf16(kPair ? 2 * BM : BM, (kPair && p.tiles_n > 1) ? (uint32_t)kBN : (uint32_t)((n_valid + 15) & ~15));
+            const uint32_t idesc = ewvit::umma_idesc_bf16(kPair ? 2 * BM : BM, p.k16 == 2 ? 128u : (kPair && p.tiles_n > 1) ? (uint32_t)kBN : (uint32_t)((n_valid + 15) & ~15));
             ewvit::mbar_wait(ewvit::smem_u32(&tempty[acc]), acc_phase ^ 1);
             ewvit::tc_fence_after();
             if (lane == 0) EWVIT_TRACE(1, tt, 1);
@@ -431,13 +438,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint64_t b_desc = ewvit::umma_desc_sw128(p.b_res ? smem_base + p.bres_off + kb * kBTileB : a_addr + kTileBytes);
                 const uint32_t ebar = ewvit::smem_u32(&empty[stage]);
                 const uint32_t first = kb > kb0 ? 1u : 0u;
-                if (p.flat3 && p.k16) {
-                    // 16 channels per pixel: tap (dy = kb, dx) is ONE K = 16 MMA on the window shifted by dx rows of 32 bytes
+                if (p.flat3 && p.k16 == 2) {
+                    // three wavelet levels side by side: a pixel is one 64-byte row of 32 channels = [level 0..2][9 subbands] (+ 5 of
+                    // padding), i.e. TWO K steps: level 0 lives in step 0, level 2 in step 1, level 1 straddles both.  Per tap
+                    // (dy = kb, dx) TWO K = 16, N = 128 MMAs read the 64B-swizzled window at a start address shifted by dx rows:
+                    // step 0 against [level-0 | level-1] copies of the shared head weights into accumulator columns [0, 128), step 1
+                    // against [level-1 | level-2] copies into columns [64, 192).  (An MMA costs its operand reads -- 4 KB of A whatever
+                    // N is -- so twelve N = 64 MMAs per slot ran at ~70 cycles each and bounded the kernel.)  Columns [64, 128) are
+                    // written by both steps: the very first step-1 MMA of a tile is split so that [128, 192) starts from zero.
                     if (ewvit::elect_one()) {
+                        const uint32_t idesc64 = ewvit::umma_idesc_bf16(BM, 64u);
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx)
-                            ewvit::umma_bf16(d_tmem, ewvit::umma_desc_sw32(a_addr + dx * 32),
-                                             ewvit::umma_desc_sw32(smem_base + p.bres_off + (kb * 3 + dx) * kBTileB), idesc, (dx > 0 || kb > kb0) ? 1u : 0u);
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const uint64_t ad = ewvit::umma_desc_sw64(a_addr + dx * 64);
+                            const uint32_t bt = smem_base + p.bres_off + (uint32_t)((kb * 3 + dx) * 2) * kBTileB;
+                            const bool first = dx == 0 && kb == kb0;
+                            ewvit::umma_bf16(d_tmem, ad, ewvit::umma_desc_sw32(bt), idesc, first ? 0u : 1u);
+                            if (first) {
+                                ewvit::umma_bf16(d_tmem + 64u, ad + 2, ewvit::umma_desc_sw32(bt + kBTileB), idesc64, 1u);
+                                ewvit::umma_bf16(d_tmem + 128u, ad + 2, ewvit::umma_desc_sw32(bt + kBTileB + 64u * 32u), idesc64, 0u);
+                            } else {
+                                ewvit::umma_bf16(d_tmem + 64u, ad + 2, ewvit::umma_desc_sw32(bt + kBTileB), idesc, 1u);
+                            }
+                        }
                         ewvit::umma_commit(ebar);
                     }
                 } else if (p.flat3) {
@@ -1206,6 +1229,7 @@ int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
 int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const GemmParams &p, int epi, cudaStream_t stream,
                 int bn = BN) {
     if (epi == EPI_CONV && p.pair) return launch_gemm_t<EPI_CONV, false, 128, 0, true>(tmA, tmB, tmC, p, stream);
+    if (epi == EPI_CONV && bn == 192) return launch_gemm_t<EPI_CONV, false, 192>(tmA, tmB, tmC, p, stream);   // three-level MWT head conv
     if (epi == EPI_CONV) return launch_gemm_t<EPI_CONV, false, 128>(tmA, tmB, tmC, p, stream);
     if (epi == EPI_BB) {
         const int fast = (g_dbg & 256) ? 0 : (p.act == 4 && !p.residual_bf16) ? 1 : p.act == 0 ? 2 : 0;
@@ -1243,7 +1267,7 @@ ewvit_encode_tiled_fn ewvit_get_encode_tiled() {
 }
 
 int ewvit_make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t *dims,
-                         const uint64_t *strides_bytes, const uint32_t *box, const uint32_t *estr, bool swizzle128, bool swizzle32) {
+                         const uint64_t *strides_bytes, const uint32_t *box, const uint32_t *estr, bool swizzle128, bool swizzle32, bool swizzle64) {
     ewvit_encode_tiled_fn enc = ewvit_get_encode_tiled();
     EWVIT_REQUIRE(enc != nullptr, EWVIT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[5], gstr[5];
@@ -1256,7 +1280,7 @@ int ewvit_make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uin
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i + 1];
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bdim,
                      es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     EWVIT_REQUIRE(r == CUDA_SUCCESS, EWVIT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
@@ -1350,9 +1374,14 @@ extern "C" int ewvit_linear_bf16(const void *a, const void *w, int64_t M, int N,
     return EWVIT_OK;
 }
 
-extern "C" int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, int wd, int cin, int cout, int stride,
-                                  int in_padded, const float *scale, const float *shift, int relu, void *y,
+extern "C" int ewvit_conv3x3_bf16(const void *x_base, int x_ldc, int x_coff, const void *w, int n, int h, int wd, int cin, int cout,
+                                  int stride, int in_padded, const float *scale, const float *shift, int relu, void *y,
                                   int y_ldc, int y_coff, int out_padded, int force_tiled, void *stream) {
+    EWVIT_REQUIRE(x_base && x_ldc >= cin && x_coff >= 0 && x_coff + cin <= x_ldc && x_ldc % 8 == 0 && x_coff % 8 == 0, EWVIT_ERR_INVALID_ARG,
+                  "ewvit_conv3x3_bf16: bad input channel pitch/offset (x_ldc=%d x_coff=%d cin=%d)", x_ldc, x_coff, cin);
+    EWVIT_REQUIRE(x_ldc == cin || (stride == 1 && in_padded && out_padded && !force_tiled), EWVIT_ERR_UNSUPPORTED,
+                  "ewvit_conv3x3_bf16: a channel slice of a wider tensor is implemented for the stride-1 padded-flat path only");
+    const void *x = static_cast<const __nv_bfloat16 *>(x_base) + x_coff;
     EWVIT_REQUIRE(n >= 0 && h > 0 && wd > 0 && cin > 0 && cout > 0, EWVIT_ERR_INVALID_ARG, "ewvit_conv3x3_bf16: bad sizes");
     if (n == 0) return EWVIT_OK;
     EWVIT_REQUIRE(x && w && y, EWVIT_ERR_INVALID_ARG, "ewvit_conv3x3_bf16: NULL pointer");
@@ -1389,7 +1418,7 @@ extern "C" int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, in
     const bool flat = (stride == 1) && in_padded && out_padded && !force_tiled;
     if (flat) {
         const long long rows = (long long)n * hin * win;
-        uint64_t dims[2] = {(uint64_t)cin, (uint64_t)rows}, str[2] = {2, (uint64_t)cin * 2};
+        uint64_t dims[2] = {(uint64_t)cin, (uint64_t)rows}, str[2] = {2, (uint64_t)x_ldc * 2};
         uint32_t box[2] = {BK, BM};
         rc = ewvit_make_tmap_bf16(&tmA, x, 2, dims, str, box, nullptr);
         if (rc != EWVIT_OK) return rc;
@@ -1450,6 +1479,20 @@ extern "C" int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, in
         p.out_wp = wo + 2 * p.out_pad;
         p.out_img_rows = (long long)(ho + 2 * p.out_pad) * p.out_wp;
         p.M = (long long)n * p.out_img_rows;
+        if (!(g_dbg & 128) && p.tiles_m >= 2 && p.tiles_n == 1) {
+            // CTA pairs here, too (freq_conv / freq_pool, stride 2): half of every weight tile per CTA, ring slot 32 -> 24 KB
+            // (7 stages instead of 5 in the 184 KB operand region) and 2 KB less shared-memory traffic per MMA
+            p.pair = 1;
+            p.b_half = BN / 2;
+            uint64_t dimsb[2] = {(uint64_t)9 * cin, (uint64_t)cout}, strb[2] = {2, (uint64_t)9 * cin * 2};
+            uint32_t boxh[2] = {BK, (uint32_t)p.b_half};
+            rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, strb, boxh, nullptr);
+            if (rc != EWVIT_OK) return rc;
+            p.b_tile_bytes = p.b_half * BK * 2;
+            p.stage_bytes = kTileBytes + p.b_tile_bytes;
+            p.stages = Cfg<EPI_CONV, false>::kOperandBytes / p.stage_bytes;
+            if (p.stages > 8) p.stages = 8;
+        }
         const int off = in_padded ? 0 : -1;
         for (int dy = 0; dy < 3; ++dy)
             for (int dx = 0; dx < 3; ++dx) {
@@ -1655,39 +1698,40 @@ extern "C" int ewvit_conv_nhwc_bf16_ex(const void *x, const void *w, int n, int 
     return conv_nhwc_impl(x, w, n, h, wd, cin, cout, ksize, stride, bias, act, residual, y, in_padded ? 1 : 0, out_padded ? 1 : 0, stream);
 }
 
-// Tensor-core head of one wavelet level, step 2 (mwt.py:84-86): the three per-colour Conv2d(3->18, 3x3, p1)+BN+ReLU as
-// ONE block-diagonal 9(16) -> 54(64) conv.  The input is the padded-flat [n, h+2, wd+2, 16] bf16 tensor of
-// ewvit_mwt_upsample_fwd.  With 16 channels per pixel a pixel is exactly one 32-byte row = one MMA K step, so the conv is nine
-// K = 16 MMAs per 128-pixel tile: per vertical tap ONE window of 136 pixel rows (4.3 KB, 32B-swizzled) is fetched and its three
-// horizontal taps read it at start addresses shifted by 0 / 32 / 64 bytes: 13 KB per tile instead of the 48 KB of three
-// overlapping 64-wide windows.  Measured: the kernel time did NOT change (0.19 ms per 256 frames either way) -- a tiled TMA load
-// costs ~3 cycles per box ROW whatever the row length (408 rows per tile in both layouts), and with the loads replaced by
-// cp.async copies (tried, dropped) the per-tile cost of the epilogue (~2400 cycles per 128 x 64 tile and group) is next in line.
-// Round 2: with the epilogue switched off the kernel still needs 322 of its 372 us per 512 frames (tools/trace_head.py), and a
-// variant with four epilogue groups (64-column tiles, 16 epilogue warps) measured no faster: the producer's ~1700 cycles per tile
-// (three 136-row boxes of 32-byte rows) are the bound.
-//   w [64, 144] bf16: w[g*18+oc][(dy*3 + dx)*16 + g*3+ic] = seperate[g].weight[oc][ic][dy][dx], zero elsewhere
-//   scale/shift [64] fp32 (folded BN, zeros past 54);  y [n, h+2, wd+2, 64] bf16 padded-flat (border written as zeros)
-extern "C" int ewvit_mwt_head_conv_fwd(const void *up, const void *w, int n, int h, int wd, const float *scale, const float *shift,
-                                       void *y, void *stream) {
-    EWVIT_REQUIRE(n >= 0 && h > 0 && wd > 0, EWVIT_ERR_INVALID_ARG, "ewvit_mwt_head_conv_fwd: bad sizes");
+// Tensor-core head of the wavelet levels, step 2 (mwt.py:84-86): the three per-colour Conv2d(3->18, 3x3, p1)+BN+ReLU as ONE
+// block-diagonal 9 -> 54(64) conv per level.
+// All three wavelet levels in ONE launch.  `up` is the padded-flat [n, h+2, wd+2, 32] bf16 tensor of ewvit_mwt_upsample3_fwd: a pixel
+// is one 64-byte row = channels [9 l, 9 l + 9) for level l (+ 5 channels of zero padding) = two MMA K steps.  Per 128-pixel tile and
+// vertical tap ONE 64B-swizzled window of 136 pixel rows is fetched and 6 MMAs (3 horizontal taps x 2 K steps, N = 128) read it at
+// start addresses shifted by dx rows; level l accumulates in TMEM columns [64 l, 64 l + 64).  The single-level kernel fetched 408
+// window rows and issued nine MMAs per tile and LEVEL and was bound by those fixed costs (~1700 cycles per tile); here the same rows and
+// eighteen MMAs serve the three levels (versions with 128-byte pixel rows or with one N = 64 MMA per level and K step were slower:
+// 2.7 GB of L2 -> shared window traffic / ~70 cycles per MMA whatever its N), and the 128 x 192 epilogue runs on four groups of warps.
+//   w [128, 288] bf16, w[r][((dy*3 + dx)*2 + step)*16 + kk]: rows [0, 64) of step 0 = level 0, rows [64, 128) of step 0 and rows
+//     [0, 64) of step 1 = level 1, rows [64, 128) of step 1 = level 2; within a block row g*18+oc holds seperate[g].weight[oc][ic][dy][dx]
+//     where channel 16*step + kk of a pixel is subband 3g+ic of that level, zero elsewhere (engine.pack_head3_weights);
+//   scale/shift [192] fp32 = the 64-entry folded BN repeated per level;
+//   y [n, h+2, wd+2, 192] bf16 padded-flat: channels [64 l, 64 l + 54) = head of level l, the rest and the border zero.
+extern "C" int ewvit_mwt_head_conv3_fwd(const void *up, const void *w, int n, int h, int wd, const float *scale, const float *shift,
+                                        void *y, void *stream) {
+    EWVIT_REQUIRE(n >= 0 && h > 0 && wd > 0, EWVIT_ERR_INVALID_ARG, "ewvit_mwt_head_conv3_fwd: bad sizes");
     if (n == 0) return EWVIT_OK;
-    EWVIT_REQUIRE(up && w && scale && shift && y, EWVIT_ERR_INVALID_ARG, "ewvit_mwt_head_conv_fwd: NULL pointer");
+    EWVIT_REQUIRE(up && w && scale && shift && y, EWVIT_ERR_INVALID_ARG, "ewvit_mwt_head_conv3_fwd: NULL pointer");
     EWVIT_REQUIRE(ewvit_aligned16(up) && ewvit_aligned16(w) && ewvit_aligned16(y), EWVIT_ERR_INVALID_ARG,
-                  "ewvit_mwt_head_conv_fwd: pointers must be 16-byte aligned");
+                  "ewvit_mwt_head_conv3_fwd: pointers must be 16-byte aligned");
     int rc = ewvit_check_device();
     if (rc != EWVIT_OK) return rc;
-    const int hin = h + 2, win = wd + 2, cpx = 16, cout = 64;
+    const int hin = h + 2, win = wd + 2, cpx = 32, cout = 64, levels = 3, tiles_per_tap = 2, brows = 128;
     const long long rows = (long long)n * hin * win;
     GemmParams p = {};
     p.a_mode = A_FLAT;
-    p.flat3 = 1;                  // one ring slot per vertical tap: a window of 136 pixel rows shared by its three horizontal taps
-    p.k16 = 1;                    // ... of 32 bytes each (16 channels = one MMA K step), 32B-swizzled
+    p.flat3 = 1;
+    p.k16 = 2;                    // three levels per pixel row
     p.chunks_per_tap = 1;
     p.num_kb = 3;
     p.kb_per_split = 3;
     p.splits = 1;
-    p.N = cout;
+    p.N = levels * cout;
     p.tiles_n = 1;
     p.M = rows;
     p.tiles_m = (int)((rows + BM - 1) / BM);
@@ -1695,27 +1739,29 @@ extern "C" int ewvit_mwt_head_conv_fwd(const void *up, const void *w, int n, int
         for (int dx = 0; dx < 3; ++dx) p.tap_a0[dy * 3 + dx] = (dy - 1) * win + (dx - 1);
     p.pad_hp = hin;
     p.pad_wp = win;
-    p.out = y; p.out_fp32 = 0; p.ldo = cout; p.col_off = 0;
+    p.out = y; p.out_fp32 = 0; p.ldo = levels * cout; p.col_off = 0;
     p.scale = scale; p.shift = shift; p.act = 1;
     CUtensorMap tmA, tmB, tmC;
     {
         uint64_t dims[2] = {(uint64_t)cpx, (uint64_t)rows}, str[2] = {2, (uint64_t)cpx * 2};
         uint32_t box[2] = {(uint32_t)cpx, (uint32_t)kFlat3Rows};
-        rc = ewvit_make_tmap_bf16(&tmA, up, 2, dims, str, box, nullptr, false, /*swizzle32=*/true);
+        rc = ewvit_make_tmap_bf16(&tmA, up, 2, dims, str, box, nullptr, false, false, /*swizzle64=*/true);
         if (rc != EWVIT_OK) return rc;
-        uint64_t dimsb[2] = {(uint64_t)9 * cpx, (uint64_t)cout}, strb[2] = {2, (uint64_t)9 * cpx * 2};
-        uint32_t boxb[2] = {(uint32_t)cpx, (uint32_t)cout};
+        const uint64_t kw = (uint64_t)9 * tiles_per_tap * 16;
+        uint64_t dimsb[2] = {kw, (uint64_t)brows}, strb[2] = {2, kw * 2};
+        uint32_t boxb[2] = {16u, (uint32_t)brows};
         rc = ewvit_make_tmap_bf16(&tmB, w, 2, dimsb, strb, boxb, nullptr, false, /*swizzle32=*/true);
         if (rc != EWVIT_OK) return rc;
     }
-    p.b_tile_bytes = cout * cpx * 2;                     // 2 KB per (dy, dx) tap
-    p.stage_bytes = kFlat3Rows * cpx * 2;                // 4352 bytes = 17 swizzle atoms of 256 bytes
-    p.b_res = 1;                                         // all nine weight tiles (18 KB) stay resident
-    p.stages = kStages;
-    p.bres_off = p.stages * p.stage_bytes;
-    rc = make_out_tmap(&tmC, y, true, rows, cout, 0, 0, 0);
+    p.b_tile_bytes = brows * 16 * 2;                     // 4 KB per (tap, K step)
+    p.stage_bytes = kFlat3Rows * cpx * 2;                // 8704 bytes = 17 swizzle atoms of 512 bytes
+    p.b_res = 1;                                         // all 18 weight tiles (72 KB) stay resident
+    p.stages = (Cfg<EPI_CONV, false, 192>::kOperandBytes - 9 * tiles_per_tap * p.b_tile_bytes) / p.stage_bytes;
+    if (p.stages > kStages) p.stages = kStages;
+    p.bres_off = (p.stages * p.stage_bytes + 1023) & ~1023;
+    rc = make_out_tmap(&tmC, y, true, rows, levels * cout, 0, 0, 0);
     if (rc != EWVIT_OK) return rc;
-    return launch_gemm(tmA, tmB, tmC, p, EPI_CONV, (cudaStream_t)stream);
+    return launch_gemm(tmA, tmB, tmC, p, EPI_CONV, (cudaStream_t)stream, 192);
 }
 
 // Debug aid: when non-NULL, CTA 0 of every subsequent GEMM/conv launch writes clock64 stamps of its warp roles

@@ -1,8 +1,8 @@
 // MWT glue kernels around the tensor-core convs.
 //
-//  * mwt_upsample: high-frequency subbands of one level -> bilinear upsample to the level-1 grid (F.interpolate,
-//    mwt.py:79-81) -> bf16 "padded-flat" NHWC [N, H+2, W+2, 16], the input of the block-diagonal head conv
-//    (ewvit_mwt_head_conv_fwd in ewvit_gemm.cu: the three per-colour Conv2d(3->18,3x3,p1)+BN+ReLU of mwt.py:84-86).
+//  * mwt_upsample3: high-frequency subbands of the three levels -> bilinear upsample to the level-1 grid (F.interpolate,
+//    mwt.py:79-81) -> bf16 "padded-flat" NHWC [N, H+2, W+2, 32], the input of the block-diagonal head conv
+//    (ewvit_mwt_head_conv3_fwd in ewvit_gemm.cu: the three per-colour Conv2d(3->18,3x3,p1)+BN+ReLU of mwt.py:84-86).
 //  * maxpool2x2 (freq_pool[0], mwt.py:39) and the global average pool (freq_pool[4], mwt.py:43) on NHWC bf16.
 #include "ewvit_common.cuh"
 
@@ -19,105 +19,114 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
 }
 
 
-// ---- tensor-core head, step 1: high-frequency subbands of one level -> bilinear upsample (F.interpolate,
-//      align_corners=False, mwt.py:79-81; identity at level 1) -> bf16 "padded-flat" NHWC [n, hout+2, wout+2, 16]
-//      (channels 0..8 = the nine subbands in the reference's colour-major order, 9..15 zero; the one-pixel border is
-//      never written and must be zero).  One thread per output pixel: 32 bytes out, coalesced.  Step 2 is the
-//      block-diagonal 9 -> 54 conv on the tensor cores (ewvit_mwt_head_conv_fwd).
-__global__ void __launch_bounds__(256) mwt_upsample_kernel(const float *__restrict__ hf, __nv_bfloat16 *__restrict__ y, long long n,
-                                                           int hin, int win, int hout, int wout, float ry, float rx) {
-    const long long total = n * hout * wout;
-    const bool same = (hin == hout) && (win == wout);
-    const long long plane = (long long)hin * win;
-    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        const int ox = (int)(i % wout);
-        const long long t = i / wout;
-        const int oy = (int)(t % hout);
-        const long long img = t / hout;
-        const float *src = hf + img * 9 * plane;
-        float v[9];
-        if (same) {
-#pragma unroll
-            for (int c = 0; c < 9; ++c) v[c] = __ldg(src + c * plane + (long long)oy * win + ox);
-        } else {
-            int ya, yb, xa, xb;
-            float ly, lx;
-            src_index(oy, ry, hin, ya, yb, ly);
-            src_index(ox, rx, win, xa, xb, lx);
-#pragma unroll
-            for (int c = 0; c < 9; ++c) {
-                const float *pc = src + c * plane;
-                const float v00 = __ldg(pc + ya * win + xa), v01 = __ldg(pc + ya * win + xb);
-                const float v10 = __ldg(pc + yb * win + xa), v11 = __ldg(pc + yb * win + xb);
-                v[c] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-            }
-        }
-        uint4 lo, hi;
-        __nv_bfloat162 b;
-        b = __floats2bfloat162_rn(v[0], v[1]); lo.x = *reinterpret_cast<uint32_t *>(&b);
-        b = __floats2bfloat162_rn(v[2], v[3]); lo.y = *reinterpret_cast<uint32_t *>(&b);
-        b = __floats2bfloat162_rn(v[4], v[5]); lo.z = *reinterpret_cast<uint32_t *>(&b);
-        b = __floats2bfloat162_rn(v[6], v[7]); lo.w = *reinterpret_cast<uint32_t *>(&b);
-        b = __floats2bfloat162_rn(v[8], 0.f);  hi.x = *reinterpret_cast<uint32_t *>(&b);
-        hi.y = hi.z = hi.w = 0u;
-        uint4 *dst = reinterpret_cast<uint4 *>(y + ((img * (hout + 2) + oy + 1) * (wout + 2) + ox + 1) * 16);
-        dst[0] = lo;
-        dst[1] = hi;
-    }
-}
-
-// Upsampling variant (hin < hout): a CTA owns `rows_out` output rows of one frame, stages the source rows those need for
-// all nine planes in shared memory with coalesced loads and gathers the four bilinear taps from there -- the direct kernel
-// above issues 36 scattered global loads per output pixel and is L1-gather bound (115 us per level against ~35 us of HBM
-// time).  Same arithmetic, same results.
-__global__ void __launch_bounds__(256) mwt_upsample_smem_kernel(const float *__restrict__ hf, __nv_bfloat16 *__restrict__ y, int hin,
-                                                                int win, int hout, int wout, float ry, float rx, int rows_out,
-                                                                int src_rows_max) {
-    extern __shared__ __align__(16) float up_s[];            // [9][src_rows_max][win]
+// ---- all three levels at once: hf_l [n, 9, h >> (l-1), w >> (l-1)] fp32 (l = 1..3, sizes relative to the level-1 grid h x w)
+//      -> up [n, h+2, w+2, 32] bf16 padded-flat, a pixel = one 64-byte row: channel 9 l' + c = subband c of level l' + 1 upsampled
+//      to the level-1 grid (identity for level 1), channels 27..31 zero.  This is the operand layout of ewvit_mwt_head_conv3_fwd,
+//      which serves the three levels from ONE window fetch.  A CTA owns `rows_out` output rows of one frame and stages the source
+//      rows of the three levels in shared memory (coalesced loads).  A lane computes the 27 values of one pixel (warp-uniform
+//      control flow); the warp then transposes its 32 pixels x 64 bytes through a swizzled shared-memory buffer so that every
+//      store instruction writes 512 contiguous bytes.
+struct Up3Params {
+    const float *hf[3];
+    int hin[3], win[3], rows_max[3], off[3];     // source size, staged rows per plane, float offset of the level in shared memory
+    float ry[3], rx[3];
+    int tr_off;                                  // float offset of the per-warp transposition buffers (8 x 2 KB)
+};
+__global__ void __launch_bounds__(256) mwt_upsample3_kernel(const Up3Params p, __nv_bfloat16 *__restrict__ y, int hout, int wout,
+                                                            int rows_out) {
+    extern __shared__ __align__(16) float up3_s[];
     const int parts = (hout + rows_out - 1) / rows_out;
     const long long img = blockIdx.x / parts;
     const int part = blockIdx.x % parts;
     const int oy0 = part * rows_out, oy1 = min(hout, oy0 + rows_out);
-    int ya0, yb_, ya1, yb1;
-    float l_;
-    src_index(oy0, ry, hin, ya0, yb_, l_);
-    src_index(oy1 - 1, ry, hin, ya1, yb1, l_);
-    const int nrows = yb1 - ya0 + 1;                          // <= src_rows_max (checked on the host)
-    const float *src = hf + img * 9 * (long long)hin * win;
-    const int row_f4 = win >> 2;                              // win % 4 == 0 (checked on the host)
-    for (int i = threadIdx.x; i < 9 * nrows * row_f4; i += 256) {
-        const int c = i / (nrows * row_f4), rem = i - c * (nrows * row_f4);
-        const int r = rem / row_f4, q = rem - r * row_f4;
-        reinterpret_cast<float4 *>(up_s + ((size_t)c * src_rows_max + r) * win)[q] =
-            __ldg(reinterpret_cast<const float4 *>(src + ((long long)c * hin + ya0 + r) * win) + q);
-    }
-    __syncthreads();
-    const int npix = (oy1 - oy0) * wout;
-    for (int i = threadIdx.x; i < npix; i += 256) {
-        const int oy = oy0 + i / wout, ox = i % wout;
-        int ya, yb, xa, xb;
-        float ly, lx;
-        src_index(oy, ry, hin, ya, yb, ly);
-        src_index(ox, rx, win, xa, xb, lx);
-        float v[9];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int ya0[3];
 #pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        int yb_, ya1, yb1;
+        float l_;
+        src_index(oy0, p.ry[l], p.hin[l], ya0[l], yb_, l_);
+        src_index(oy1 - 1, p.ry[l], p.hin[l], ya1, yb1, l_);
+        const int nrows = yb1 - ya0[l] + 1;                   // <= rows_max[l] (sized on the host)
+        const int win = p.win[l], rmax = p.rows_max[l];
+        const float *src = p.hf[l] + img * 9 * (long long)p.hin[l] * win;
+        float *dst = up3_s + p.off[l];
+        // the staged rows of a plane are ONE contiguous block in global and in shared memory: asynchronous 16-byte copies, all in
+        // flight at once (a load-then-store loop left one request per warp outstanding: 0.5 ms per 512 frames, latency-bound)
+        const bool vec = (win & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+        const int blk = nrows * win;                           // floats per plane
         for (int c = 0; c < 9; ++c) {
-            const float *pc = up_s + (size_t)c * src_rows_max * win;
-            const float v00 = pc[(ya - ya0) * win + xa], v01 = pc[(ya - ya0) * win + xb];
-            const float v10 = pc[(yb - ya0) * win + xa], v11 = pc[(yb - ya0) * win + xb];
-            v[c] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+            const float *sp = src + ((long long)c * p.hin[l] + ya0[l]) * win;
+            float *dp = dst + (size_t)c * rmax * win;
+            if (vec) {
+                const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dp);
+                for (int q = threadIdx.x; q < (blk >> 2); q += 256)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (uint32_t)q * 16u), "l"(sp + 4 * q) : "memory");
+            } else {
+                for (int x = threadIdx.x; x < blk; x += 256) dp[x] = __ldg(sp + x);
+            }
         }
-        uint4 lo, hi;
-        __nv_bfloat162 b;
-        b = __floats2bfloat162_rn(v[0], v[1]); lo.x = *reinterpret_cast<uint32_t *>(&b);
-        b = __floats2bfloat162_rn(v[2], v[3]); lo.y = *reinterpret_cast<uint32_t *>(&b);
-        b = __floats2bfloat162_rn(v[4], v[5]); lo.z = *reinterpret_cast<uint32_t *>(&b);
-        b = __floats2bfloat162_rn(v[6], v[7]); lo.w = *reinterpret_cast<uint32_t *>(&b);
-        b = __floats2bfloat162_rn(v[8], 0.f);  hi.x = *reinterpret_cast<uint32_t *>(&b);
-        hi.y = hi.z = hi.w = 0u;
-        uint4 *dst = reinterpret_cast<uint4 *>(y + ((img * (hout + 2) + oy + 1) * (wout + 2) + ox + 1) * 16);
-        dst[0] = lo;
-        dst[1] = hi;
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const uint32_t tr = (uint32_t)__cvta_generic_to_shared(up3_s + p.tr_off) + (uint32_t)warp * 2048u;
+    const int npix = (oy1 - oy0) * wout;
+    for (int base = warp * 32; base < npix; base += 256) {
+        const int pix = base + lane;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        if (pix < npix) {
+            const int oy = oy0 + pix / wout, ox = pix % wout;
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                const int win = p.win[l], rmax = p.rows_max[l];
+                const float *lb = up3_s + p.off[l];
+                if (p.hin[l] == hout && win == wout) {
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) v[9 * l + c] = lb[((size_t)c * rmax + (oy - ya0[l])) * win + ox];
+                } else {
+                    int ya, yb, xa, xb;
+                    float ly, lx;
+                    src_index(oy, p.ry[l], p.hin[l], ya, yb, ly);
+                    src_index(ox, p.rx[l], win, xa, xb, lx);
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        const float *pc = lb + (size_t)c * rmax * win;
+                        const float v00 = pc[(ya - ya0[l]) * win + xa], v01 = pc[(ya - ya0[l]) * win + xb];
+                        const float v10 = pc[(yb - ya0[l]) * win + xa], v11 = pc[(yb - ya0[l]) * win + xb];
+                        v[9 * l + c] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+                    }
+                }
+            }
+        }
+        // lane = pixel: chunk k (8 channels) goes to position k ^ ((lane >> 1) & 3) of the pixel's 64-byte row (conflict-free both ways)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
+                w4[i] = *reinterpret_cast<const uint32_t *>(&b);
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tr + (uint32_t)lane * 64u + (uint32_t)((k ^ ((lane >> 1) & 3)) << 4)),
+                         "r"(w4[0]), "r"(w4[1]), "r"(w4[2]), "r"(w4[3]) : "memory");
+        }
+        __syncwarp();
+        // lane = (pixel within a group of 8, chunk): one store instruction writes 8 pixels x 64 bytes = 512 contiguous bytes
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int pp = 8 * j + (lane >> 2), k = lane & 3;
+            uint4 val;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                         : "r"(tr + (uint32_t)pp * 64u + (uint32_t)((k ^ ((pp >> 1) & 3)) << 4)) : "memory");
+            const int gp = base + pp;
+            if (gp < npix) {
+                const int oy = oy0 + gp / wout, ox = gp % wout;
+                *reinterpret_cast<uint4 *>(y + ((img * (hout + 2) + oy + 1) * (wout + 2) + ox + 1) * 32 + k * 8) = val;
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -161,40 +170,43 @@ __global__ void gap_kernel(const __nv_bfloat16 *__restrict__ x, float *__restric
 
 
 
-extern "C" int ewvit_mwt_upsample_fwd(const float *hf, int n, int hin, int win, int hout, int wout, void *y, void *stream) {
-    EWVIT_REQUIRE(n >= 0 && hin > 0 && win > 0 && hout > 0 && wout > 0, EWVIT_ERR_INVALID_ARG, "ewvit_mwt_upsample_fwd: bad sizes");
+extern "C" int ewvit_mwt_upsample3_fwd(const float *hf1, const float *hf2, const float *hf3, int n, int h, int wd, void *up, void *stream) {
+    EWVIT_REQUIRE(n >= 0 && h > 0 && wd > 0 && h % 4 == 0 && wd % 4 == 0, EWVIT_ERR_INVALID_ARG,
+                  "ewvit_mwt_upsample3_fwd: the level-1 grid must be a multiple of 4 in both directions (got %dx%d)", h, wd);
     if (n == 0) return EWVIT_OK;
-    EWVIT_REQUIRE(hf && y && ewvit_aligned16(y), EWVIT_ERR_INVALID_ARG, "ewvit_mwt_upsample_fwd: NULL or misaligned pointer");
+    EWVIT_REQUIRE(hf1 && hf2 && hf3 && up && ewvit_aligned16(up), EWVIT_ERR_INVALID_ARG, "ewvit_mwt_upsample3_fwd: NULL or misaligned pointer");
+    EWVIT_REQUIRE(n <= (1 << 22), EWVIT_ERR_UNSUPPORTED, "ewvit_mwt_upsample3_fwd: too many frames");
     int rc = ewvit_check_device();
     if (rc != EWVIT_OK) return rc;
-    if ((hin < hout || win < wout) && win % 4 == 0 && ewvit_aligned16(hf) && n <= (1 << 22)) {
-        // staged variant: ~half a frame of output rows per CTA when that keeps the nine source planes under ~64 KB
-        int rows_out = hout;
-        auto src_rows = [&](int ro) { return (int)((long long)ro * hin / hout) + 3; };
-        while (rows_out > 8 && (size_t)9 * src_rows(rows_out) * win * 4 > 64 * 1024) rows_out = (rows_out + 1) / 2;
-        const int srm = src_rows(rows_out);
-        const size_t smem = (size_t)9 * srm * win * 4;
-        if (smem <= 96 * 1024) {
-            static bool attr_set[64] = {false};
-            int dev = 0;
-            EWVIT_CUDA_OK(cudaGetDevice(&dev));
-            if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-                EWVIT_CUDA_OK(cudaFuncSetAttribute(mwt_upsample_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-                if (dev >= 0 && dev < 64) attr_set[dev] = true;
-            }
-            const int parts = (hout + rows_out - 1) / rows_out;
-            mwt_upsample_smem_kernel<<<(unsigned)((long long)n * parts), 256, smem, (cudaStream_t)stream>>>(
-                hf, static_cast<__nv_bfloat16 *>(y), hin, win, hout, wout, (float)hin / (float)hout, (float)win / (float)wout, rows_out, srm);
-            EWVIT_LAUNCH_OK();
-            return EWVIT_OK;
+    Up3Params p;
+    p.hf[0] = hf1; p.hf[1] = hf2; p.hf[2] = hf3;
+    int rows_out = 8;
+    size_t smem = 0;
+    for (;;) {
+        int off = 0;
+        for (int l = 0; l < 3; ++l) {
+            p.hin[l] = h >> l; p.win[l] = wd >> l;
+            p.ry[l] = (float)p.hin[l] / (float)h; p.rx[l] = (float)p.win[l] / (float)wd;
+            p.rows_max[l] = (rows_out >> l) + 3;                      // source rows ya(oy0) .. yb(oy1 - 1) of the band
+            p.off[l] = off;
+            off += (9 * p.rows_max[l] * p.win[l] + 3) & ~3;          // keep every level 16-byte aligned
         }
+        p.tr_off = off;
+        off += 8 * 2048 / (int)sizeof(float);                        // transposition buffers: 8 warps x 32 pixels x 64 bytes
+        smem = (size_t)off * sizeof(float);
+        if (smem <= 96 * 1024 || rows_out == 1) break;
+        rows_out >>= 1;
     }
-    const long long total = (long long)n * hout * wout;
-    long long blocks = (total + 255) / 256;
-    const long long cap = (long long)ewvit_num_sms() * 16;
-    if (blocks > cap) blocks = cap;
-    mwt_upsample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(hf, static_cast<__nv_bfloat16 *>(y), n, hin, win, hout, wout,
-                                                                           (float)hin / (float)hout, (float)win / (float)wout);
+    EWVIT_REQUIRE(smem <= 200 * 1024, EWVIT_ERR_UNSUPPORTED, "ewvit_mwt_upsample3_fwd: rows of %d pixels do not fit the staging buffer", wd);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    EWVIT_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        EWVIT_CUDA_OK(cudaFuncSetAttribute(mwt_upsample3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const int parts = (h + rows_out - 1) / rows_out;
+    mwt_upsample3_kernel<<<(unsigned)((long long)n * parts), 256, smem, (cudaStream_t)stream>>>(p, static_cast<__nv_bfloat16 *>(up), h, wd, rows_out);
     EWVIT_LAUNCH_OK();
     return EWVIT_OK;
 }

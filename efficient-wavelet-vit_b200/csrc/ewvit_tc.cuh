@@ -16,7 +16,7 @@ ewvit_encode_tiled_fn ewvit_get_encode_tiled();
 // dims[i] elements, strides_bytes[i] for i>=1 (stride of dim 0 is the element size), box[i], estr[i].
 int ewvit_make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t *dims,
                          const uint64_t *strides_bytes, const uint32_t *box, const uint32_t *estr, bool swizzle128 = true,
-                         bool swizzle32 = false);
+                         bool swizzle32 = false, bool swizzle64 = false);
 
 #ifdef __CUDACC__
 namespace ewvit {
@@ -57,6 +57,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
     d |= (uint64_t)(256u >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)6 << 61;
+    return d;
+}
+
+// Rows of 64 bytes (32 bf16 = two MMA K steps), 64B swizzle: 8-row groups are 512 bytes apart, layout type 4.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(512u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
     return d;
 }
 
@@ -123,6 +133,12 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void *tmap,
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(leader_addr(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const void *tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(leader_addr(bar))
         : "memory");
 }
 // arrive on a barrier of the leader CTA from either CTA of the pair.  Default (.release.cta) semantics on purpose: what the arrive

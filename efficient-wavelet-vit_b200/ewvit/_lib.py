@@ -28,7 +28,7 @@ SIGNATURES = {
     "ewvit_dwt3_haar_fwd": (c_int, [c_void_p, c_int64, c_int, c_int] + [c_void_p] * 6 + [c_void_p]),
     "ewvit_linear_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int,
                                   c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
-    "ewvit_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+    "ewvit_conv3x3_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ewvit_maxpool2x2_nhwc_bf16": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
     "ewvit_gap_nhwc_bf16": (c_int, [P, c_int64, c_int, c_int, P, c_int64, P]),
@@ -50,8 +50,8 @@ SIGNATURES = {
     "ewvit_dwconv_nhwc_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "ewvit_dwconv_pool_parts": (c_int, [c_int, c_int, c_int, c_int]),
     "ewvit_conv1x1_gated_nhwc_bf16": (c_int, [P, P, c_int, P, c_int, c_int, c_int, c_int, P, c_int, P, P, P]),
-    "ewvit_mwt_upsample_fwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),
-    "ewvit_mwt_head_conv_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P]),
+    "ewvit_mwt_upsample3_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
+    "ewvit_mwt_head_conv3_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P]),
     "ewvit_binary_metrics_fwd": (c_int, [P, P, c_int, P, P]),
     "ewvit_debug_set_trace": (c_int, [P]),
     "ewvit_debug_set_flags": (c_int, [c_int]),

@@ -109,6 +109,23 @@ def _to_device(obj, dev):
 
 
 # ------------------------------------------------------------------------------------------ MWT
+def pack_head3_weights(wbd):
+    """Block-diagonal head weights [64, 3, 3, 16] fp32 (output g*18+oc, tap, subband 3g+ic) -> bf16 [128, 288] for
+    ``ewvit_mwt_head_conv3_fwd``: a pixel of its input holds channel 9*l + c for level l, subband c, i.e. two K steps of 16
+    channels; per tap and K step one [128, 16] tile whose row halves are the shared weights of the two levels living in that
+    step (step 0: levels 0 | 1, step 1: levels 1 | 2), placed at the positions their subbands occupy, zero elsewhere."""
+    out = torch.zeros((2, 64, 9, 2, 16), dtype=torch.float32)      # [row half, out, tap, step, kk]
+    w9 = wbd.reshape(64, 9, 16)[:, :, :9]                          # [out, tap, subband]
+    for step in range(2):
+        for half in range(2):
+            lvl = step + half
+            for kk in range(16):
+                c = step * 16 + kk - 9 * lvl
+                if 0 <= c < 9:
+                    out[half, :, :, step, kk] = w9[:, :, c]
+    return out.reshape(128, 288).to(torch.bfloat16).contiguous()
+
+
 class MwtRunner:
     """Native ``MWT.forward`` (levels = 3, in_channels = 3).  ``sd`` holds the module's own keys
     (``hf_conv.seperate.0.0.weight`` ...) as CUDA tensors."""
@@ -132,11 +149,13 @@ class MwtRunner:
         for g in range(3):
             wg = self.head_w[g]                                   # [18, 3, ky, kx]
             wbd[g * 18:(g + 1) * 18, :, :, g * 3:(g + 1) * 3] = wg.permute(0, 2, 3, 1)
-        self.head_wbd = wbd.reshape(64, 144).to(torch.bfloat16).contiguous()
         self.head_scale64 = torch.zeros(64, dtype=torch.float32, device=dev)
         self.head_shift64 = torch.zeros(64, dtype=torch.float32, device=dev)
         self.head_scale64[:54] = self.head_scale
         self.head_shift64[:54] = self.head_shift
+        self.head_w3 = pack_head3_weights(wbd)
+        self.head_scale192 = self.head_scale64.repeat(3).contiguous()      # the head is shared by the three levels
+        self.head_shift192 = self.head_shift64.repeat(3).contiguous()
         self.fus_w = _conv_w_tapmajor(sd["hf_conv.fusion.0.weight"], 64)
         self.fus_scale, self.fus_shift = _fold_bn(sd, "hf_conv.fusion.0.", "hf_conv.fusion.1.")
         self.ms_w = _conv_w_tapmajor(sd["multiscale_fusion.0.weight"])
@@ -166,8 +185,8 @@ class MwtRunner:
             full = {
                 "n": n,
                 "hf": [torch.empty((n, 3, 3, h >> l, w >> l), dtype=torch.float32, device=dev) for l in (1, 2, 3)],
-                "up": torch.zeros((n, h1 + 2, w1 + 2, 16), dtype=bf, device=dev),        # zero border, kept zero
-                "head": torch.zeros((n, h1 + 2, w1 + 2, 64), dtype=bf, device=dev),      # zero border, kept zero
+                "up": torch.zeros((n, h1 + 2, w1 + 2, 32), dtype=bf, device=dev),        # channel 9 l + c per pixel; zero border, kept zero
+                "head": torch.zeros((n, h1 + 2, w1 + 2, 192), dtype=bf, device=dev),     # [level][64] per pixel; zero border, kept zero
                 "cat": torch.empty((n, h1 + 2, w1 + 2, 3 * d), dtype=bf, device=dev),
                 "ms": torch.empty((n, h1 + 2, w1 + 2, d), dtype=bf, device=dev),
                 "fc": torch.empty((n, h2, w2, d), dtype=bf, device=dev),
@@ -189,14 +208,13 @@ class MwtRunner:
         hf = ws["hf"]
         with stage("mwt.dwt3"):
             ops.dwt3_haar(frames, out={"hf1": hf[0], "hf2": hf[1], "hf3": hf[2]}, want=("hf1", "hf2", "hf3"), norm=norm)
-        for lvl in range(3):
-            with stage("mwt.head"):
-                hfl = hf[lvl].view(n, 9, h >> (lvl + 1), w >> (lvl + 1))
-                ops.mwt_upsample(hfl, ws["up"], h1, w1)
-                ops.mwt_head_conv(ws["up"], self.head_wbd, self.head_scale64, self.head_shift64, ws["head"], h1, w1)
-            with stage("mwt.hf_fusion"):
+        with stage("mwt.head"):       # all three levels: one upsample launch, one block-diagonal tensor-core conv
+            ops.mwt_upsample3(*[hf[lvl].view(n, 9, h >> (lvl + 1), w >> (lvl + 1)) for lvl in range(3)], ws["up"], h1, w1)
+            ops.mwt_head_conv3(ws["up"], self.head_w3, self.head_scale192, self.head_shift192, ws["head"], h1, w1)
+        with stage("mwt.hf_fusion"):
+            for lvl in range(3):        # level lvl = channels [64 lvl, 64 lvl + 64) of every head pixel
                 ops.conv3x3_bf16(ws["head"], self.fus_w, n, h1, w1, 1, True, self.fus_scale, self.fus_shift, True,
-                                 ws["cat"], lvl * d, True)
+                                 ws["cat"], lvl * d, True, x_coff=64 * lvl)
         with stage("mwt.multiscale"):
             ops.conv3x3_bf16(ws["cat"], self.ms_w, n, h1, w1, 1, True, self.ms_scale, self.ms_shift, True, ws["ms"], 0, True)
         with stage("mwt.freq_conv"):

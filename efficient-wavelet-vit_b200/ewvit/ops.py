@@ -135,17 +135,19 @@ def linear_bf16(a, w, scale=None, shift=None, act=None, residual=None, out=None,
     return out
 
 
-def conv3x3_bf16(x, w, n, h, wd, stride, in_padded, scale, shift, relu, y, y_coff, out_padded, force_tiled=False):
+def conv3x3_bf16(x, w, n, h, wd, stride, in_padded, scale, shift, relu, y, y_coff, out_padded, force_tiled=False, x_coff=0):
     """3x3/pad-1 conv on NHWC bf16 (see include/ewvit.h).  x, y are flat/ND contiguous buffers laid out as
-    [n, h(+2), wd(+2), cin] / [n, ho(+2), wo(+2), ldc]; w is [cout, 3, 3, cin]."""
+    [n, h(+2), wd(+2), x_ldc] / [n, ho(+2), wo(+2), ldc]; w is [cout, 3, 3, cin]; the conv reads channels
+    [x_coff, x_coff + cin) of x (x_ldc = x.shape[-1])."""
     _check_bf16(x, "x")
     _check_bf16(w, "w", 4)
     _check_bf16(y, "y")
     cout, _, _, cin = w.shape
     ldc = y.shape[-1]
+    x_ldc = x.shape[-1] if x.dim() > 1 else cin
     hin, win = (h + 2, wd + 2) if in_padded else (h, wd)
-    if x.numel() != n * hin * win * cin:
-        raise EwvitError(f"conv3x3_bf16: x has {x.numel()} elements, expected {n}x{hin}x{win}x{cin}")
+    if x.numel() != n * hin * win * x_ldc:
+        raise EwvitError(f"conv3x3_bf16: x has {x.numel()} elements, expected {n}x{hin}x{win}x{x_ldc}")
     ho, wo = (h - 1) // stride + 1, (wd - 1) // stride + 1
     hop, wop = (ho + 2, wo + 2) if out_padded else (ho, wo)
     if y.numel() != n * hop * wop * ldc:
@@ -153,7 +155,7 @@ def conv3x3_bf16(x, w, n, h, wd, stride, in_padded, scale, shift, relu, y, y_cof
     scale = _f32_or_none(scale, "scale", cout)
     shift = _f32_or_none(shift, "shift", cout)
     with torch.cuda.device(x.device):
-        check(load().ewvit_conv3x3_bf16(x.data_ptr(), w.data_ptr(), n, h, wd, cin, cout, stride, int(in_padded),
+        check(load().ewvit_conv3x3_bf16(x.data_ptr(), x_ldc, x_coff, w.data_ptr(), n, h, wd, cin, cout, stride, int(in_padded),
                                         _ptr(scale), _ptr(shift), int(relu), y.data_ptr(), ldc, y_coff,
                                         int(out_padded), int(force_tiled), _stream()), "ewvit_conv3x3_bf16")
     return y
@@ -165,32 +167,35 @@ def _check_f32(t, name):
         raise EwvitError(f"{name} must be a contiguous fp32 CUDA tensor")
 
 
-def mwt_upsample(hf, up, hout, wout):
-    """hf [n,9,hin,win] fp32 -> up [n,hout+2,wout+2,16] bf16 (interior written, channels 9..15 zero)."""
-    _check_f32(hf, "hf")
+def mwt_upsample3(hf1, hf2, hf3, up, h, wd):
+    """hf_l [n,9,h>>(l-1),wd>>(l-1)] fp32 -> up [n,h+2,wd+2,32] bf16: channels [9l, 9l+9) = level l+1 on the h x wd grid."""
+    for t, nm in ((hf1, "hf1"), (hf2, "hf2"), (hf3, "hf3")):
+        _check_f32(t, nm)
     _check_bf16(up, "up")
-    n, c9, hin, win = hf.shape
-    if c9 != 9 or up.numel() != n * (hout + 2) * (wout + 2) * 16:
-        raise EwvitError("mwt_upsample: expects 9 subband planes and an [n,hout+2,wout+2,16] output")
-    with torch.cuda.device(hf.device):
-        check(load().ewvit_mwt_upsample_fwd(hf.data_ptr(), n, hin, win, hout, wout, up.data_ptr(), _stream()), "ewvit_mwt_upsample_fwd")
+    n = hf1.shape[0]
+    if tuple(hf1.shape) != (n, 9, h, wd) or tuple(hf2.shape) != (n, 9, h // 2, wd // 2) or tuple(hf3.shape) != (n, 9, h // 4, wd // 4) \
+            or up.numel() != n * (h + 2) * (wd + 2) * 32:
+        raise EwvitError("mwt_upsample3: expects [n,9,h,wd], [n,9,h/2,wd/2], [n,9,h/4,wd/4] and an [n,h+2,wd+2,32] output")
+    with torch.cuda.device(hf1.device):
+        check(load().ewvit_mwt_upsample3_fwd(hf1.data_ptr(), hf2.data_ptr(), hf3.data_ptr(), n, h, wd, up.data_ptr(), _stream()),
+              "ewvit_mwt_upsample3_fwd")
     return up
 
 
-def mwt_head_conv(up, w, scale, shift, y, h, wd):
-    """up [n,h+2,wd+2,16] bf16, w [64,144] bf16, scale/shift [64] fp32 -> y [n,h+2,wd+2,64] bf16 (see include/ewvit.h)."""
+def mwt_head_conv3(up, w, scale, shift, y, h, wd):
+    """up [n,h+2,wd+2,32] bf16, w [128,288] bf16, scale/shift [192] fp32 -> y [n,h+2,wd+2,192] bf16 (see include/ewvit.h)."""
     _check_bf16(up, "up")
     _check_bf16(w, "w", 2)
     _check_bf16(y, "y")
     _check_f32(scale, "scale")
     _check_f32(shift, "shift")
-    n = up.numel() // ((h + 2) * (wd + 2) * 16)
-    if up.numel() != n * (h + 2) * (wd + 2) * 16 or y.numel() != n * (h + 2) * (wd + 2) * 64 or tuple(w.shape) != (64, 144) \
-            or scale.numel() != 64 or shift.numel() != 64:
-        raise EwvitError("mwt_head_conv: shape mismatch")
+    n = up.numel() // ((h + 2) * (wd + 2) * 32)
+    if up.numel() != n * (h + 2) * (wd + 2) * 32 or y.numel() != n * (h + 2) * (wd + 2) * 192 or tuple(w.shape) != (128, 288) \
+            or scale.numel() != 192 or shift.numel() != 192:
+        raise EwvitError("mwt_head_conv3: shape mismatch")
     with torch.cuda.device(up.device):
-        check(load().ewvit_mwt_head_conv_fwd(up.data_ptr(), w.data_ptr(), n, h, wd, scale.data_ptr(), shift.data_ptr(), y.data_ptr(),
-                                             _stream()), "ewvit_mwt_head_conv_fwd")
+        check(load().ewvit_mwt_head_conv3_fwd(up.data_ptr(), w.data_ptr(), n, h, wd, scale.data_ptr(), shift.data_ptr(), y.data_ptr(),
+                                              _stream()), "ewvit_mwt_head_conv3_fwd")
     return y
 
 

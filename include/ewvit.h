@@ -115,7 +115,9 @@ EWVIT_API int ewvit_linear_bf16(const void *a, const void *w, int64_t M, int N, 
  * ReLU triples at reference network/mwt.py:33-36 freq_conv, :40-42 freq_pool, :60-64 hf_conv.fusion,
  * :68-72 multiscale_fusion).
  *
- *   x  NHWC bf16: [n, h, wd, cin], or with in_padded = 1 [n, h+2, wd+2, cin] carrying an explicit zero border
+ *   x  NHWC bf16: [n, h, wd, x_ldc], or with in_padded = 1 [n, h+2, wd+2, x_ldc] carrying an explicit zero border; the conv
+ *      reads the cin channels starting at channel x_coff of every pixel (x_ldc = cin, x_coff = 0: a dense tensor; a slice of a
+ *      wider tensor -- one level of the three-level MWT head -- is implemented for the stride-1 padded-flat path)
  *   w  [cout, 3, 3, cin] bf16 (tap-major K: k = (ky*3 + kx)*cin + c)
  *   y  NHWC bf16 with channel pitch y_ldc, written at channel offset y_coff (lets three producers fill
  *      one concatenated buffer, mwt.py:113): [n, ho, wo, y_ldc], or with out_padded = 1
@@ -126,7 +128,7 @@ EWVIT_API int ewvit_linear_bf16(const void *a, const void *w, int64_t M, int N, 
  * pixels only (a padded y must have been zeroed once by the caller).  force_tiled = 1 forces the box path.
  * Needs cin % 64 == 0 and cout % 128 == 0.
  * ------------------------------------------------------------------------------------------- */
-EWVIT_API int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, int wd, int cin, int cout,
+EWVIT_API int ewvit_conv3x3_bf16(const void *x, int x_ldc, int x_coff, const void *w, int n, int h, int wd, int cin, int cout,
                                  int stride, int in_padded, const float *scale, const float *shift, int relu,
                                  void *y, int y_ldc, int y_coff, int out_padded, int force_tiled, void *stream);
 
@@ -134,19 +136,24 @@ EWVIT_API int ewvit_conv3x3_bf16(const void *x, const void *w, int n, int h, int
  * MWT glue  (rows a-3, a-4)
  * ------------------------------------------------------------------------------------------- */
 
-/* High-frequency head of one wavelet level: reference network/mwt.py:77-86 -- `hf[0].reshape(B, 3C, h, w)` (colour-major),
- * `F.interpolate(..., mode='bilinear')` to the level-1 grid (align_corners=False; identity when hin == hout), then the three
- * per-colour Conv2d(3->18,3x3,p1)+BN+ReLU of hf_conv['seperate'] and their channel concat -- in two steps:
- *   1. ewvit_mwt_upsample_fwd: hf [n, 9, hin, win] fp32 -> bilinear upsample (identity when hin == hout) ->
- *      up [n, hout+2, wout+2, 16] bf16 padded-flat NHWC (channels 9..15 zero).  Only interior pixels are written: the
- *      one-pixel border must be zero (zero the buffer once).
- *   2. ewvit_mwt_head_conv_fwd: the three Conv2d(3->18,3x3,p1)+BN+ReLU as one block-diagonal conv on the tensor cores.
- *      w [64, 144] bf16 with w[g*18+oc][(dy*3 + dx)*16 + g*3+ic] = seperate[g].weight[oc][ic][dy][dx] (zero elsewhere),
- *      scale/shift [64] fp32 (folded bias + eval BatchNorm, zeros past channel 54),
- *      y [n, h+2, wd+2, 64] bf16 padded-flat NHWC (channels 54..63 and the border come out as zeros). */
-EWVIT_API int ewvit_mwt_upsample_fwd(const float *hf, int n, int hin, int win, int hout, int wout, void *up, void *stream);
-EWVIT_API int ewvit_mwt_head_conv_fwd(const void *up, const void *w, int n, int h, int wd, const float *scale,
-                                      const float *shift, void *y, void *stream);
+/* High-frequency head of the three wavelet levels (model.py:35 levels = 3): reference network/mwt.py:77-86 per level --
+ * `hf[0].reshape(B, 3C, h, w)` (colour-major), `F.interpolate(..., mode='bilinear')` to the level-1 grid (align_corners=False;
+ * identity at level 1), then the three per-colour Conv2d(3->18,3x3,p1)+BN+ReLU of hf_conv['seperate'] and their channel concat --
+ * for all levels in two launches (what one MWT.wavelet_transform loop, mwt.py:107-111, computes before hf_conv.fusion):
+ *   1. ewvit_mwt_upsample3_fwd: hf1 [n, 9, h, wd], hf2 [n, 9, h/2, wd/2], hf3 [n, 9, h/4, wd/4] fp32 (h x wd = the level-1 grid,
+ *      multiples of 4) -> up [n, h+2, wd+2, 32] bf16 padded-flat NHWC: channel 9 l + c = subband c of level l + 1 upsampled to
+ *      h x wd, channels 27..31 zero.  Interior pixels only: the one-pixel border must be zero (zero the buffer once).
+ *   2. ewvit_mwt_head_conv3_fwd: the convs as one block-diagonal conv on the tensor cores.
+ *      w [128, 288] bf16 = per tap (dy*3 + dx) and K step one [128, 16] tile, w[r][((dy*3 + dx)*2 + step)*16 + kk]:
+ *      rows [0, 64) of step 0 = level 1, rows [64, 128) of step 0 and rows [0, 64) of step 1 = level 2, rows [64, 128) of step 1 =
+ *      level 3; inside a 64-row block row g*18+oc holds seperate[g].weight[oc][ic][dy][dx] where channel 16*step + kk of a pixel is
+ *      subband 3g+ic of that level, zero elsewhere (the head is shared by the levels); scale/shift [192] fp32 = the 64-entry
+ *      folded bias + eval BatchNorm (zeros past channel 54) repeated three times; y [n, h+2, wd+2, 192] bf16 padded-flat: channels
+ *      [64 l, 64 l + 54) = the 54-channel head of level l + 1 (the input of hf_conv.fusion, read in place through x_ldc / x_coff
+ *      of ewvit_conv3x3_bf16), everything else and the border zero. */
+EWVIT_API int ewvit_mwt_upsample3_fwd(const float *hf1, const float *hf2, const float *hf3, int n, int h, int wd, void *up, void *stream);
+EWVIT_API int ewvit_mwt_head_conv3_fwd(const void *up, const void *w, int n, int h, int wd, const float *scale,
+                                       const float *shift, void *y, void *stream);
 
 /* nn.MaxPool2d(2, 2) on NHWC bf16 (freq_pool[0], mwt.py:39): x [n,h,w,c] -> y [n,h/2,w/2,c]. */
 EWVIT_API int ewvit_maxpool2x2_nhwc_bf16(const void *x, int64_t n, int h, int w, int c, void *y, void *stream);

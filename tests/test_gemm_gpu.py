@@ -75,7 +75,7 @@ def test_linear_rejects_bad_shapes(ops):
                         torch.zeros(100, 64, dtype=torch.bfloat16, device="cuda"))   # N % 128 != 0
 
 
-def _conv_case(ops, n, h, w, cin, cout, stride, in_padded, out_padded, force_tiled, seed, ldc=None, coff=0):
+def _conv_case(ops, n, h, w, cin, cout, stride, in_padded, out_padded, force_tiled, seed, ldc=None, coff=0, x_ldc=None, x_coff=0):
     x = _randn((n, cin, h, w), seed).bfloat16()
     wt = _randn((cout, cin, 3, 3), seed + 1, (9 * cin) ** -0.5).bfloat16()
     scale, shift = _randn((cout,), seed + 2).abs() + 0.5, _randn((cout,), seed + 3)
@@ -91,8 +91,12 @@ def _conv_case(ops, n, h, w, cin, cout, stride, in_padded, out_padded, force_til
     # the row-shift path writes its own zero border; the box path expects a pre-zeroed padded buffer
     fill = 0.0 if (out_padded and not row_shift) else 7.0
     y = torch.full(yshape, fill, dtype=torch.bfloat16, device="cuda")
+    if x_ldc:       # the conv reads a channel slice of a wider tensor; the other channels hold large values that must not leak in
+        wide = torch.full(xh.shape[:-1] + (x_ldc,), 100.0, dtype=torch.bfloat16)
+        wide[..., x_coff:x_coff + cin] = xh
+        xh = wide
     ops.conv3x3_bf16(xh.cuda().contiguous(), wt.permute(0, 2, 3, 1).contiguous().cuda(), n, h, w, stride, in_padded,
-                     scale.cuda(), shift.cuda(), True, y, coff, out_padded, force_tiled)
+                     scale.cuda(), shift.cuda(), True, y, coff, out_padded, force_tiled, x_coff=x_coff)
     got = y.float().cpu()
     inner = got[:, 1:-1, 1:-1] if out_padded else got
     _close(inner[..., coff:coff + cout].permute(0, 3, 1, 2), ref, bf16_out=True)
@@ -112,6 +116,18 @@ def test_conv_stride1_row_shift_path(ops, cin, cout):
 
 def test_conv_stride1_into_concat_buffer(ops):
     _conv_case(ops, 2, 12, 16, 64, 128, 1, True, True, False, seed=31, ldc=384, coff=128)
+
+
+@pytest.mark.parametrize("x_coff", [0, 64, 128])
+def test_conv_stride1_reads_channel_slice(ops, x_coff):
+    """hf_conv.fusion reads level l of the three-level head tensor in place (x_ldc = 192, x_coff = 64 l)."""
+    _conv_case(ops, 2, 12, 16, 64, 128, 1, True, True, False, seed=35 + x_coff, ldc=384, coff=128, x_ldc=192, x_coff=x_coff)
+
+
+def test_conv_channel_slice_needs_the_row_shift_path(ops):
+    from ewvit import EwvitError
+    with pytest.raises(EwvitError):
+        _conv_case(ops, 1, 12, 16, 64, 128, 2, True, False, False, seed=36, x_ldc=192, x_coff=64)
 
 
 def test_conv_stride1_full_112(ops):

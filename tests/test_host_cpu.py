@@ -152,8 +152,10 @@ def test_backbone_layout_plan_and_window_weight_packing():
     assert float(pk[:, 144:192].abs().max()) == 0.0 and float(pk[:, 192 + 144:384].abs().max()) == 0.0
 
 
-def test_mwt_head_block_diagonal_packing(model):
-    """The tensor-core head's [64, 144] matrix: w[18g+oc][(dy*3 + dx)*16 + 3g+ic] = seperate[g].weight[oc][ic][dy][dx]."""
+def test_mwt_head_three_level_weight_packing(model):
+    """The three-level tensor-core head's [128, 288] matrix (include/ewvit.h, ewvit_mwt_head_conv3_fwd): per tap and K step a
+    [128, 16] tile; rows [0, 64) / [64, 128) of step s belong to level s / s + 1; channel 16 s + kk of a pixel is subband
+    9-relative c = 16 s + kk - 9 level of that level, and row 18 g + oc holds seperate[g].weight[oc][ic][dy][dx] for c = 3 g + ic."""
     from ewvit import engine
     sd = {k[len("dama.mwt."):]: v.detach().float() for k, v in model.state_dict().items() if k.startswith("dama.mwt.")}
     run = engine.MwtRunner.__new__(engine.MwtRunner)
@@ -161,12 +163,31 @@ def test_mwt_head_block_diagonal_packing(model):
         engine.MwtRunner.__init__(run, sd)
     except Exception:
         pytest.skip("MwtRunner needs CUDA tensors for its remaining packs")
-    wbd = run.head_wbd.float().view(64, 3, 3, 16)
-    for g in range(3):
-        wg = sd[f"hf_conv.seperate.{g}.0.weight"]
-        for (oc, ic, dy, dx) in ((0, 0, 0, 0), (17, 2, 2, 2), (9, 1, 1, 0)):
-            assert float(wbd[18 * g + oc, dy, dx, 3 * g + ic]) == float(wg[oc, ic, dy, dx].bfloat16())
-    assert float(wbd[54:].abs().max()) == 0.0 and float(wbd[..., 9:].abs().max()) == 0.0
+    w3 = run.head_w3.float().view(2, 64, 3, 3, 2, 16)          # [row half, out, dy, dx, step, kk]
+    seen = torch.zeros_like(w3, dtype=torch.bool)
+    for step in range(2):
+        for half in range(2):
+            lvl = step + half
+            for g in range(3):
+                wg = sd[f"hf_conv.seperate.{g}.0.weight"]
+                for ic in range(3):
+                    kk = 9 * lvl + 3 * g + ic - 16 * step
+                    if not 0 <= kk < 16:
+                        continue
+                    for (oc, dy, dx) in ((0, 0, 0), (17, 2, 2), (9, 1, 0)):
+                        assert float(w3[half, 18 * g + oc, dy, dx, step, kk]) == float(wg[oc, ic, dy, dx].bfloat16())
+                    seen[half, 18 * g:18 * g + 18, :, :, step, kk] = True
+    assert float(w3[~seen].abs().max()) == 0.0                  # everything else is zero (block-diagonal, padded)
+    # every (level, subband) pair is covered exactly once over the two K steps
+    cover = torch.zeros(3, 9, dtype=torch.int32)
+    for step in range(2):
+        for half in range(2):
+            for kk in range(16):
+                c = 16 * step + kk - 9 * (step + half)
+                if 0 <= c < 9:
+                    cover[step + half, c] += 1
+    assert bool((cover == 1).all())
+    assert tuple(run.head_scale192.shape) == (192,) and torch.equal(run.head_scale192[:64], run.head_scale192[128:])
 
 
 def test_native_runner_cache_invalidation_rules(model):

@@ -56,33 +56,30 @@ def detector(manifest):
     return m.cuda().eval()
 
 
-def test_mwt_head_kernels(dama_sd, sd_cuda, frames):
-    """bilinear upsample kernel + block-diagonal tensor-core conv = per-colour 3->18 convs + BN + ReLU (mwt.py:77-86), three levels."""
+def test_mwt_head_three_levels_in_one_launch(dama_sd, sd_cuda, frames):
+    """What MwtRunner runs: one upsample launch (channel 9 l + c of a 64-byte pixel row) + one block-diagonal conv whose tile serves
+    the three levels from one window fetch ([level][64] channels per pixel), against the per-colour convs of the oracle (mwt.py:77-86)."""
     from ewvit import engine, ops
     run = engine.MwtRunner(engine._sub(sd_cuda, "dama.mwt."))
     with torch.no_grad():
         _, inter = O.mwt_forward(dama_sd, "dama.mwt.", frames, return_intermediates=True)
     out = ops.dwt3_haar(frames.cuda(), want=("hf1", "hf2", "hf3"))
-    import torch.nn.functional as F
+    hfs = [out[f"hf{l}"].view(2, 9, 224 >> l, 224 >> l) for l in (1, 2, 3)]
+    up = torch.zeros((2, 114, 114, 32), dtype=torch.bfloat16, device="cuda")
+    y = torch.full((2, 114, 114, 192), 7.0, dtype=torch.bfloat16, device="cuda")          # borders must come out as zeros
+    ops.mwt_upsample3(*hfs, up, 112, 112)
+    upc = up.float().cpu()
+    ops.mwt_head_conv3(up, run.head_w3, run.head_scale192, run.head_shift192, y, 112, 112)
+    got = y.float().cpu()
     for lvl in range(3):
-        hf = out[f"hf{lvl + 1}"]
-        # oracle: the three separate convs on the upsampled 9-channel map
         hf9 = inter[f"hf9_{lvl}"]
+        check(f"mwt_upsample3 level {lvl + 1}", upc[:, 1:-1, 1:-1, 9 * lvl:9 * lvl + 9].permute(0, 3, 1, 2), hf9, 1e-2)
         parts = [O._conv_bn_relu(hf9[:, 3 * i:3 * i + 3], dama_sd, f"dama.mwt.hf_conv.seperate.{i}.0.",
                                  f"dama.mwt.hf_conv.seperate.{i}.1.") for i in range(3)]
-        ref = torch.cat(parts, dim=1)
-        # bf16 upsampled planes -> block-diagonal conv as nine K = 16 MMAs on 32B-swizzled pixel windows
-        up = torch.zeros((2, 114, 114, 16), dtype=torch.bfloat16, device="cuda")
-        y2 = torch.full((2, 114, 114, 64), 7.0, dtype=torch.bfloat16, device="cuda")     # borders must come out as zeros
-        ops.mwt_upsample(hf.view(2, 9, hf.shape[-2], hf.shape[-1]), up, 112, 112)
-        check(f"mwt_upsample level {lvl + 1}", up.float().cpu()[:, 1:-1, 1:-1, :9].permute(0, 3, 1, 2), hf9, 1e-2)
-        assert float(up[:, :, :, 9:].abs().max()) == 0.0 and float(up[:, 0].abs().max()) == 0.0
-        ops.mwt_head_conv(up, run.head_wbd, run.head_scale64, run.head_shift64, y2, 112, 112)
-        got2 = y2.float().cpu()
-        check(f"mwt_head_conv level {lvl + 1}", got2[:, 1:-1, 1:-1, :54].permute(0, 3, 1, 2), ref, 2e-2)
-        assert float(got2[:, 1:-1, 1:-1, 54:].abs().max()) == 0.0
-        assert float(got2[:, 0].abs().max()) == 0.0 and float(got2[:, :, -1].abs().max()) == 0.0 and float(got2[:, -1].abs().max()) == 0.0
-
+        check(f"mwt_head_conv3 level {lvl + 1}", got[:, 1:-1, 1:-1, 64 * lvl:64 * lvl + 54].permute(0, 3, 1, 2), torch.cat(parts, dim=1), 2e-2)
+        assert float(got[:, 1:-1, 1:-1, 64 * lvl + 54:64 * lvl + 64].abs().max()) == 0.0
+    assert float(upc[..., 27:].abs().max()) == 0.0 and float(upc[:, 0].abs().max()) == 0.0 and float(upc[:, :, -1].abs().max()) == 0.0
+    assert float(got[:, 0].abs().max()) == 0.0 and float(got[:, :, -1].abs().max()) == 0.0 and float(got[:, -1].abs().max()) == 0.0
 
 def test_mwt_forward(dama_sd, sd_cuda, frames, golden):
     from ewvit import engine

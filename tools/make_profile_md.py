@@ -85,15 +85,16 @@ launches()
 traffic = {}
 for rep in sorted(glob.glob(os.path.join(GO, f"prof_{tag}_*.ncu-rep"))):
     name, recs = full(rep)
-    if name == "mwt512":
+    if name.startswith("mwt"):
+        frames = int(name[3:])
         # the multiscale conv is the longest launch of the capture
         def dur(r):
             v, u = r["gpu__time_duration.sum"]
             return float(v.replace(",", "")) * {"us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}.get(u, 1.0)
         top = max(recs, key=dur)
-        traffic["multiscale_512_frames"] = {
+        traffic[f"multiscale_{frames}_frames"] = {
             "dram_bytes": to_bytes(*top["dram__bytes_read.sum"]) + to_bytes(*top["dram__bytes_write.sum"]),
-            "frames": 512, "source": f"profiles/{tag}_{name}_ncu_full.md (longest launch)", "ms_under_ncu": dur(top)}
+            "frames": frames, "source": f"profiles/{tag}_{name}_ncu_full.md (longest launch)", "ms_under_ncu": dur(top)}
     if name == "dwt256":
         r = recs[0]
         traffic["dwt3_256_frames"] = {"dram_bytes": to_bytes(*r["dram__bytes_read.sum"]) + to_bytes(*r["dram__bytes_write.sum"]),
