@@ -241,7 +241,15 @@ __global__ void video_head_kernel(const float *__restrict__ a, const float *__re
         if (!src[t]) continue;
         for (int ch = j; ch < d; ch += blockDim.x) {
             float s = 0.f;
-            for (int i = 0; i < k; ++i) s += src[t][(v * k + i) * d + ch];
+            const float *pv = src[t] + v * k * d + ch;
+            for (int i0 = 0; i0 < k; i0 += 16) {        // 16 frames requested at once, summed in frame order as before
+                float tmp[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) tmp[u] = i0 + u < k ? __ldg(pv + (long long)(i0 + u) * d) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                    if (i0 + u < k) s += tmp[u];
+            }
             s /= (float)k;
             dst[t][v * d + ch] = s;
             if (t == 0) s_mean[ch] = s;
