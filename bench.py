@@ -447,7 +447,7 @@ def main():
                 # frac above 1 means this conv kernel sustains more than that matmul does, not that a physical limit was passed
                 "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "burst_peak": peaks["bf16_tflops"],
                 "frac_of_nominal_dense_bf16": achieved / 2250.0}
-    fusion_ms = stages["mwt.hf_fusion"][0]                               # three launches per step share one bracket each
+    fusion_ms = stages["mwt.hf_fusion"][0] / 3.0                         # ONE bracket per step holds the three per-level launches
     fusion_flops = 2.0 * n_frames * 112 * 112 * 128 * 9 * 64             # K padded 54 -> 64 channels
     second = {"kernel": "gemm_tc_kernel<EPI_CONV, pair> hf_conv.fusion 54(64)->128 @112x112 x3 levels (mwt.py:57-61)", "bound": "tensor",
               "achieved": fusion_flops / (fusion_ms / 1e3) / 1e12, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",

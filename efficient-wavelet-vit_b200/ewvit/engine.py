@@ -20,7 +20,7 @@ from ._lib import EwvitError
 
 BN_EPS = 1e-5
 LN_EPS = 1e-5
-MACRO_BATCH = 512          # frames per pass: bounds the MWT workspace (~17 MB / frame)
+MACRO_BATCH = 512          # frames per pass: bounds the MWT workspace (~22 MB / frame)
 
 
 class StageTimer:
@@ -169,7 +169,7 @@ class MwtRunner:
         self._ws = {}
 
     def _workspace(self, n, h, w):
-        """One grow-only workspace per frame size (~17 MB per frame): allocated for the largest n seen, smaller batches
+        """One grow-only workspace per frame size (~22 MB per frame): allocated for the largest n seen, smaller batches
         (ragged tails of the macro-batch splitter) use leading slices.  Single-stream: two concurrent forwards of one
         runner on different CUDA streams would share these buffers."""
         full = self._ws.get((h, w))
