@@ -277,8 +277,6 @@ class NativeEffNetV2:
         if any(p.device.type != "cpu" for p in features.parameters()):
             features = copy.deepcopy(features).to("cpu")
         self.ops = []
-        self.fuse_se = True         # SE gate applied inside the project conv's operand path
-        self.c24 = True             # 24 -> 24 stage-1 convs on the direct warp-MMA kernel
         self.win_w, self.cin3 = {}, {}      # op index -> window-packed weights / input channels of the 3x3 convs
         self._padbuf = {}
         mods = list(features)
@@ -321,7 +319,7 @@ class NativeEffNetV2:
                                      se.fc2.bias.detach().float().to(dev)))
                     w2, b2 = _fold_conv_bn(pr[0], pr[1])
                     # project conv: the SE gate is applied while its A operand is assembled ("conv1g")
-                    self.ops.append(("conv1g" if self.fuse_se else "conv1", w2.flatten(1).to(torch.bfloat16).to(dev).contiguous(),
+                    self.ops.append(("conv1g", w2.flatten(1).to(torch.bfloat16).to(dev).contiguous(),
                                      b2.to(dev), None, res, True))
                 else:
                     raise EwvitError(f"native backbone: unsupported block {kind}")
@@ -343,7 +341,7 @@ class NativeEffNetV2:
 
     def _is_c24(self, i):
         op = self.ops[i]
-        return self.c24 and op[0] == "conv3" and self.cin3[i] == 24 and op[1].shape[0] == 24 and op[3] == 1 and op[4] == "silu"
+        return op[0] == "conv3" and self.cin3[i] == 24 and op[1].shape[0] == 24 and op[3] == 1 and op[4] == "silu"
 
     def _plan_layouts(self, enable):
         """Per op (in_padded, out_padded).  The stride-1 3x3 convs with cin < 64 (stages 1-2 of V2-S) run fastest on
@@ -443,10 +441,7 @@ class NativeEffNetV2:
                     pooled = torch.empty((n, c), dtype=torch.float32, device=x.device)
                     x = ops.dwconv3x3(x, w, b, stride, pooled=pooled)
                 elif kind == "se":
-                    if self.fuse_se:
-                        gate = ops.se_gate(pooled, op[1], op[2], op[3], op[4], bf16=True)
-                    else:
-                        ops.se_apply(x, pooled, op[1], op[2], op[3], op[4])
+                    gate = ops.se_gate(pooled, op[1], op[2], op[3], op[4], bf16=True)      # applied inside the project conv's operand path
                 elif kind == "conv1g":
                     _, w, b, act, res, ends = op
                     x = ops.conv1x1_gated(x, gate, w, bias=b, act=act, residual=block_in if res else None)

@@ -245,3 +245,137 @@ def test_eval_with_grad_enabled_takes_the_autograd_composition(model):
         p.requires_grad_(True)
     del cuda_like
     model.train()
+
+
+class _RecordingOps:
+    """Stand-in for ``ewvit.ops`` that records the calls of a runner and returns tensors of the right shape on the CPU: the host
+    orchestration (op order, layouts, channel offsets, residual wiring) is checked without a GPU."""
+
+    def __init__(self):
+        self.calls = []
+
+    def _rec(self, name, **kw):
+        self.calls.append((name, kw))
+
+    # ---- backbone
+    def stem_conv(self, frames, w, b, out=None, out_padded=False, norm=None, same_tf=False):
+        self._rec("stem", padded=out_padded)
+        n, _, h, wd = frames.shape
+        return out if out is not None else torch.zeros(n, (h - 1) // 2 + 1, (wd - 1) // 2 + 1, w.shape[0], dtype=torch.bfloat16)
+
+    def conv_nhwc_bf16_ex(self, x, w, k, stride, cin, bias=None, act=None, residual=None, out=None, in_padded=False, out_padded=False):
+        self._rec("conv_ex", k=k, stride=stride, cin=cin, res=residual is not None, in_padded=in_padded, out_padded=out_padded)
+        assert x.shape[-1] == cin
+        if out is not None:
+            return out
+        n, h, wd = x.shape[0], x.shape[1] - 2 * in_padded, x.shape[2] - 2 * in_padded
+        return torch.zeros(n, (h - 1) // stride + 1 + 2 * out_padded, (wd - 1) // stride + 1 + 2 * out_padded, w.shape[0], dtype=torch.bfloat16)
+
+    def conv3x3_c24(self, x, w, b, residual=False):
+        self._rec("c24", res=residual)
+        return torch.zeros_like(x)
+
+    def conv_nhwc_bf16(self, x, w, k, stride, bias=None, act=None, residual=None):
+        self._rec("conv", k=k, stride=stride, res=residual is not None, act=act)
+        if residual is not None:
+            assert residual.shape[-1] == w.shape[0]
+        n, h, wd, _ = x.shape
+        return torch.zeros(n, (h - 1) // stride + 1, (wd - 1) // stride + 1, w.shape[0], dtype=torch.bfloat16)
+
+    def dwconv3x3(self, x, w, b, stride, pooled=None):
+        self._rec("dw", stride=stride)
+        n, h, wd, c = x.shape
+        assert pooled.shape == (n, c) and w.shape == (9, c)
+        return torch.zeros(n, (h - 1) // stride + 1, (wd - 1) // stride + 1, c, dtype=torch.bfloat16)
+
+    def se_gate(self, pooled, w1, b1, w2t, b2, bf16=False):
+        self._rec("se", bf16=bf16)
+        assert w1.shape[1] == pooled.shape[1] == w2t.shape[1]
+        return torch.zeros(pooled.shape, dtype=torch.bfloat16)
+
+    def conv1x1_gated(self, x, gate, w, bias=None, act=None, residual=None):
+        self._rec("conv1g", res=residual is not None)
+        assert gate.shape == (x.shape[0], x.shape[-1]) and w.shape[1] == x.shape[-1]
+        n, h, wd, _ = x.shape
+        return torch.zeros(n, h, wd, w.shape[0], dtype=torch.bfloat16)
+
+    # ---- MWT
+    def dwt3_haar(self, frames, out=None, want=None, norm=None):
+        self._rec("dwt3", want=tuple(want))
+        return out
+
+    def mwt_upsample3(self, hf1, hf2, hf3, up, h, wd):
+        self._rec("upsample3", shapes=(tuple(hf1.shape), tuple(hf2.shape), tuple(hf3.shape)), up=tuple(up.shape))
+        return up
+
+    def mwt_head_conv3(self, up, w, scale, shift, y, h, wd):
+        self._rec("head_conv3", w=tuple(w.shape), scale=scale.numel(), y=tuple(y.shape))
+        return y
+
+    def conv3x3_bf16(self, x, w, n, h, wd, stride, in_padded, scale, shift, relu, y, y_coff, out_padded, force_tiled=False, x_coff=0):
+        self._rec("conv3x3", x=tuple(x.shape), cin=w.shape[-1], cout=w.shape[0], stride=stride, y=tuple(y.shape), y_coff=y_coff, x_coff=x_coff,
+                  in_padded=in_padded, out_padded=out_padded)
+        return y
+
+    def maxpool2x2(self, x, y=None):
+        self._rec("maxpool", x=tuple(x.shape))
+        return y
+
+    def gap(self, x, y=None):
+        self._rec("gap", x=tuple(x.shape))
+        return torch.zeros(x.shape[0], x.shape[-1]) if y is None else y
+
+
+def test_native_backbone_orchestration_with_recording_ops(monkeypatch):
+    """NativeEffNetV2.forward on stubbed ops: 140 launches per forward in the torchvision order (stem, 2 direct 24->24 convs, the
+    padded-flat window path of stage 2, 30 x (expand, depthwise + squeeze, SE gate, gated project)), residuals only where the block
+    has a skip connection, [n, 7, 7, 1280] out."""
+    from torchvision.models import efficientnet_v2_s
+    from ewvit import engine
+    rec = _RecordingOps()
+    monkeypatch.setattr(engine, "ops", rec)
+    torch.manual_seed(0)
+    net = efficientnet_v2_s(weights=None).eval()
+    nb = engine.NativeEffNetV2(net.features, "cpu")
+    y = nb.forward(torch.zeros(2, 3, 224, 224))
+    assert tuple(y.shape) == (2, 7, 7, 1280)
+    names = [c[0] for c in rec.calls]
+    assert len(names) == 140 and names[0] == "stem" and names[1:3] == ["c24", "c24"]
+    assert names.count("dw") == names.count("se") == names.count("conv1g") == 30
+    for i, nm in enumerate(names):
+        if nm == "dw":
+            assert names[i + 1:i + 3] == ["se", "conv1g"] and names[i - 1] == "conv"
+    # skip connections: every non-first block of a stage (torchvision use_res_connect)
+    want_res = sum(int(b.use_res_connect) for stage in list(net.features)[1:-1] for b in stage)
+    got_res = sum(1 for nm, kw in rec.calls if kw.get("res"))
+    assert got_res == want_res
+    assert all(kw["bf16"] for nm, kw in rec.calls if nm == "se")
+
+
+def test_mwt_runner_orchestration_with_recording_ops(model, monkeypatch):
+    """MwtRunner.forward on stubbed ops: one DWT launch (HF only), ONE upsample + ONE head conv for the three levels, three fusion
+    convs reading channels [64 l, 64 l + 64) of the head tensor and writing channels [128 l, 128 l + 128) of the concat buffer
+    (mwt.py:113), multiscale, freq_conv (stride 2), max pool, pool conv (stride 2), GAP."""
+    from ewvit import engine
+    rec = _RecordingOps()
+    monkeypatch.setattr(engine, "ops", rec)
+    sd = {k[len("dama.mwt."):]: v.detach().float() for k, v in model.state_dict().items() if k.startswith("dama.mwt.")}
+    run = engine.MwtRunner(sd)
+    n = 3
+    run.forward(torch.zeros(n, 3, 224, 224))
+    names = [c[0] for c in rec.calls]
+    assert names == ["dwt3", "upsample3", "head_conv3", "conv3x3", "conv3x3", "conv3x3", "conv3x3", "conv3x3", "maxpool", "conv3x3", "gap"]
+    kw = dict(rec.calls[0][1])
+    assert kw["want"] == ("hf1", "hf2", "hf3")
+    up = rec.calls[1][1]
+    assert up["shapes"] == ((n, 9, 112, 112), (n, 9, 56, 56), (n, 9, 28, 28)) and up["up"] == (n, 114, 114, 32)
+    hc = rec.calls[2][1]
+    assert hc["w"] == (128, 288) and hc["scale"] == 192 and hc["y"] == (n, 114, 114, 192)
+    for lvl in range(3):
+        f = rec.calls[3 + lvl][1]
+        assert (f["x"], f["cin"], f["cout"], f["x_coff"], f["y_coff"], f["y"]) == ((n, 114, 114, 192), 64, 128, 64 * lvl, 128 * lvl, (n, 114, 114, 384))
+        assert f["stride"] == 1 and f["in_padded"] and f["out_padded"]
+    ms, fc, pc = rec.calls[6][1], rec.calls[7][1], rec.calls[9][1]
+    assert (ms["cin"], ms["cout"], ms["x"], ms["y"]) == (384, 128, (n, 114, 114, 384), (n, 114, 114, 128))
+    assert (fc["stride"], fc["y"], fc["in_padded"], fc["out_padded"]) == (2, (n, 56, 56, 128), True, False)
+    assert (pc["stride"], pc["x"], pc["y"]) == (2, (n, 28, 28, 128), (n, 14, 14, 128))

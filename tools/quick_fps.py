@@ -19,4 +19,4 @@ with torch.no_grad():
     e1.record()
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
-print(f"EWVIT_OVERLAP={os.environ.get('EWVIT_OVERLAP', '1')}: {ms:.3f} ms/step, {512 / ms * 1e3:.0f} frames/s, logits finite: {bool(torch.isfinite(out['logits']).all())}")
+print(f"{ms:.3f} ms/step, {512 / ms * 1e3:.0f} frames/s, logits finite: {bool(torch.isfinite(out['logits']).all())}")
