@@ -379,3 +379,77 @@ def test_mwt_runner_orchestration_with_recording_ops(model, monkeypatch):
     assert (ms["cin"], ms["cout"], ms["x"], ms["y"]) == (384, 128, (n, 114, 114, 384), (n, 114, 114, 128))
     assert (fc["stride"], fc["y"], fc["in_padded"], fc["out_padded"]) == (2, (n, 56, 56, 128), True, False)
     assert (pc["stride"], pc["x"], pc["y"]) == (2, (n, 28, 28, 128), (n, 14, 14, 128))
+
+
+def test_macro_batch_splitter_keeps_frame_order_and_chunk_positions(monkeypatch):
+    """DamaRunner.forward_frames splits B*K frames into 512-frame passes (workspace bound); every frame keeps its (b, k) slot and its
+    reference position index whatever the split (eval.py-shaped call: 8 videos x 300 frames, batch_size 8 -> 2400 frames, ragged tail)."""
+    from ewvit import engine
+    run = engine.DamaRunner.__new__(engine.DamaRunner)
+    run.dim = 4
+    run._pos_cache = {}
+    run.sfe = type("S", (), {"pos": torch.zeros(64, 512)})()
+    seen = []
+
+    def fake_process(frames, pos, norm=None):
+        seen.append(frames.shape[0])
+        tag = frames.reshape(frames.shape[0], -1)[:, 0]                 # frame id planted in the first pixel
+        f = torch.stack([tag, pos.float(), tag * 2, tag * 0 + frames.shape[0]], dim=1)
+        return f, f + 1, f + 2
+
+    monkeypatch.setattr(run, "process_frames", fake_process, raising=False)
+    b, k, bs = 8, 300, 8
+    x = torch.zeros(b, k, 3, 8, 8)
+    x[:, :, 0, 0, 0] = torch.arange(b * k, dtype=torch.float32).view(b, k)
+    fused, space, freq = run.forward_frames(x, bs)
+    assert seen == [512, 512, 512, 512, 352] and fused.shape == (b * k, 4)
+    assert torch.equal(fused[:, 0], torch.arange(b * k, dtype=torch.float32))      # order preserved
+    assert torch.equal(space, fused + 1) and torch.equal(freq, fused + 2)
+    want_pos = engine.chunk_pos_index(b, k, bs).float()
+    assert torch.equal(fused[:, 1], want_pos)
+    # the last reference chunk holds 300 - 37*8 = 4 frames per video: positions b*4 + j
+    assert want_pos.view(b, k)[3, 296:].tolist() == [12.0, 13.0, 14.0, 15.0]
+    with pytest.raises(RuntimeError):                                             # 9 videos x 8 frames per chunk = 72 > 64 rows
+        run.forward_frames(torch.zeros(9, 16, 3, 8, 8), 8)
+
+
+def test_sfe_head_orchestration_with_recording_ops(model, monkeypatch):
+    """SfeRunner.head on stubbed ops: split-K patch embedding, token assembly, then per layer LN -> qkv -> 2-token attention ->
+    out-projection(+residual) -> LN -> ff1(GELU) -> ff2(+residual), final cast of token 1 and the feat_map Linear + ReLU (sfe.py:153-173)."""
+    from ewvit import engine
+    from network._native import load_architecture_config
+    calls = []
+
+    class Ops:
+        def linear_bf16(self, a, w, scale=None, shift=None, act=None, residual=None, out=None, out_dtype=None, splits=1, workspace=None):
+            calls.append(("linear", tuple(a.shape), tuple(w.shape), act, residual is not None, splits))
+            return out if out is not None else torch.zeros(a.shape[0], w.shape[0])
+
+        def vit_assemble(self, emb, cls, pos, pos_index, out=None):
+            calls.append(("assemble", tuple(emb.shape), tuple(out.shape)))
+            return out
+
+        def layernorm_bf16(self, x, g, b, eps=1e-5, out=None, rows=None, ldx=None, d=None):
+            calls.append(("ln", g is not None, rows))
+            return out
+
+        def vit_attention(self, qkv, n, tokens, heads, dim_head, out=None):
+            calls.append(("attn", n, tokens, heads, dim_head))
+            return out
+
+    monkeypatch.setattr(engine, "ops", Ops())
+    cfg = load_architecture_config()
+    sd = {k[len("dama.sfe."):]: v.detach() for k, v in model.state_dict().items()
+          if k.startswith("dama.sfe.") and not k.startswith("dama.sfe.efficient_net.")}
+    run = engine.SfeRunner(sd, cfg, backbone=None)
+    n = 5
+    run.head(torch.zeros(n, 62720, dtype=torch.bfloat16), torch.arange(n, dtype=torch.int32))
+    kinds = [c[0] for c in calls]
+    layer = ["ln", "linear", "attn", "linear", "ln", "linear", "linear"]
+    assert kinds == ["linear", "assemble"] + layer * 2 + ["ln", "linear"]
+    assert calls[0][1:3] == ((n, 62720), (512, 62720)) and calls[0][5] > 1                  # split-K patch_to_embedding
+    qkv, out_p, ff1, ff2 = calls[3], calls[5], calls[7], calls[8]
+    assert qkv[1:3] == ((2 * n, 512), (1536, 512)) and not qkv[4]
+    assert out_p[2] == (512, 512) and out_p[4] and ff1[2] == (2048, 512) and ff1[3] == "gelu" and ff2[2] == (512, 2048) and ff2[4]
+    assert calls[4] == ("attn", n, 2, 8, 64)
+    assert calls[-2] == ("ln", False, n) and calls[-1][2] == (128, 512) and calls[-1][3] == "relu"
