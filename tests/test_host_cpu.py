@@ -453,3 +453,34 @@ def test_sfe_head_orchestration_with_recording_ops(model, monkeypatch):
     assert out_p[2] == (512, 512) and out_p[4] and ff1[2] == (2048, 512) and ff1[3] == "gelu" and ff2[2] == (512, 2048) and ff2[4]
     assert calls[4] == ("attn", n, 2, 8, 64)
     assert calls[-2] == ("ln", False, n) and calls[-1][2] == (128, 512) and calls[-1][3] == "relu"
+
+
+def test_head3_packing_reproduces_the_per_colour_convs_in_the_kernels_algebra(model):
+    """CPU emulation of what ewvit_mwt_head_conv3_fwd computes from `pack_head3_weights`: a pixel row holds channel 9 l + c; per tap the
+    K step 0 (channels 0..15) multiplies the [level 0 | level 1] tile into accumulator columns [0, 128) and K step 1 (channels 16..31)
+    the [level 1 | level 2] tile into columns [64, 192).  The result must equal the reference's three per-colour Conv2d(3 -> 18) of
+    every level (mwt.py:84-86, before BatchNorm/ReLU)."""
+    import torch.nn.functional as F
+    from ewvit import engine
+    sd = {k[len("dama.mwt."):]: v.detach().float() for k, v in model.state_dict().items() if k.startswith("dama.mwt.")}
+    run = engine.MwtRunner(sd)
+    w3 = run.head_w3.float().view(128, 9, 2, 16)                          # [row, tap, step, kk]
+    g = torch.Generator().manual_seed(5)
+    h = w = 10
+    hf = [torch.randn(1, 9, h, w, generator=g).bfloat16().float() for _ in range(3)]      # upsampled subbands of the three levels
+    up = torch.zeros(1, h + 2, w + 2, 32)
+    for lvl in range(3):
+        up[:, 1:-1, 1:-1, 9 * lvl:9 * lvl + 9] = hf[lvl].permute(0, 2, 3, 1)
+    acc = torch.zeros(h, w, 192)
+    for dy in range(3):
+        for dx in range(3):
+            win = up[0, dy:dy + h, dx:dx + w]                              # [h, w, 32] = the tap's shifted window
+            tap = dy * 3 + dx
+            acc[..., 0:128] += win[..., 0:16] @ w3[:, tap, 0].t()
+            acc[..., 64:192] += win[..., 16:32] @ w3[:, tap, 1].t()
+    for lvl in range(3):
+        ref = torch.cat([F.conv2d(hf[lvl][:, 3 * i:3 * i + 3], sd[f"hf_conv.seperate.{i}.0.weight"].bfloat16().float(), padding=1)
+                         for i in range(3)], dim=1)[0].permute(1, 2, 0)     # [h, w, 54], bias/BN live in the epilogue's scale/shift
+        got = acc[..., 64 * lvl:64 * lvl + 54]
+        assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+        assert float(acc[..., 64 * lvl + 54:64 * lvl + 64].abs().max()) == 0.0
